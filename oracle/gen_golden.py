@@ -1,0 +1,189 @@
+"""Generate tests/golden/*.npz by running the REFERENCE itself (imported from /root/reference) on
+the seeded inputs of tests/golden/inputs.py.  Run in the build container only (the GPU box has no
+/root/reference); the outputs are committed.  TEST INFRASTRUCTURE ONLY.
+
+    python oracle/gen_golden.py [section ...]      sections: ops nets step   (default: all)
+"""
+import inspect
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("DFMIR_REFERENCE", "/root/reference")
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, GOLD)
+import inputs as gi  # noqa: E402
+
+
+def import_reference():
+    """The three shims of SURVEY.md 8c; no reference source is modified."""
+    inspect.getargspec = lambda f: inspect.getfullargspec(f)[:4]   # modelio.py:14 (removed in py3.11)
+    torch.nn.Module.cuda = lambda self, *a, **k: self              # registration_model.py:98,100
+    torch.Tensor.cuda = lambda self, *a, **k: self                 # registration_model.py:148
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+def save(name, **arrays):
+    path = os.path.join(GOLD, name + ".npz")
+    meta = {"torch_version": np.array(torch.__version__)}
+    np.savez_compressed(path, **arrays, **meta)
+    print(f"  {name}.npz  {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def gen_ops():
+    import_reference()
+    import torch.nn.functional as nnf
+    from models.voxelmorph.torchvoxelmorph import layers as rl
+    from util.losses import NCC_Loss, Grad_Loss
+    from models.registration_model import smooothing_loss, REGISTRATIONModel
+
+    # ---- warp: nearest-mode indices (observed through index-ramp sources), linear values, and the
+    # normalised grid the reference hands to F.grid_sample (captured, not recomputed)
+    captured = {}
+    real_gs = nnf.grid_sample
+
+    def spy(src, grid, **kw):
+        captured["grid"] = grid.detach().clone()
+        return real_gs(src, grid, **kw)
+
+    out = {}
+    for name, shape, sigma, seed in gi.WARP_CASES:
+        flow = gi.flow(seed, 1, shape, sigma)
+        ramps = gi.index_ramps(1, shape)
+        img = gi.image(seed + 100, 1, shape)
+        st_lin = rl.SpatialTransformer(shape)
+        st_nn = rl.SpatialTransformer(shape, mode='nearest')
+        rl.nnf.grid_sample = spy
+        y_lin = st_lin(t(img), t(flow)).numpy()
+        rl.nnf.grid_sample = real_gs
+        ngrid = captured["grid"].numpy()          # (1,*S,nd) xyz order
+        nd = len(shape)
+        ngrid = np.moveaxis(ngrid, -1, 1)[:, ::-1]  # back to (1,nd,*S), ij order
+        y_nn = st_nn(t(ramps), t(flow)).numpy()   # sampled index per axis, 0 where out of bounds
+        ones = st_nn(torch.ones(1, 1, *shape), t(flow)).numpy()  # 1 in bounds, 0 outside
+        out[name + "/nearest_idx"] = y_nn.astype(np.int16)
+        out[name + "/nearest_inb"] = ones.astype(np.uint8)
+        out[name + "/linear"] = y_lin
+        if sigma in (0.0, 1e-5) or name in ("w3d_32x40x48_s3", "w2d_37x53_s2"):
+            out[name + "/ngrid"] = np.ascontiguousarray(ngrid)
+    for name, shape, seed in gi.HALF_CASES:
+        flow = gi.half_integer_flow(seed, 1, shape)
+        st_nn = rl.SpatialTransformer(shape, mode='nearest')
+        out[name + "/nearest_idx"] = st_nn(t(gi.index_ramps(1, shape)), t(flow)).numpy().astype(np.int16)
+        out[name + "/nearest_inb"] = st_nn(torch.ones(1, 1, *shape), t(flow)).numpy().astype(np.uint8)
+    save("warp", **out)
+
+    # ---- warp backward (autograd through the reference module)
+    out = {}
+    for name, shape, sigma, seed in [("b2d", (48, 64), 2.0, 41), ("b3d", (12, 16, 20), 1.5, 42)]:
+        nd = len(shape)
+        src = t(gi.image(seed, 2, shape, C=2)).requires_grad_()
+        flow = t(gi.flow(seed + 1, 2, shape, sigma)).requires_grad_()
+        gout = t(gi.weights(seed + 2, (2, 2, *shape), 1.0))
+        y = rl.SpatialTransformer(shape)(src, flow)
+        y.backward(gout)
+        out[name + "/out"] = y.detach().numpy()
+        out[name + "/d_src"] = src.grad.numpy()
+        out[name + "/d_flow"] = flow.grad.numpy()
+    save("warp_bwd", **out)
+
+    # ---- VecInt + ResizeTransform (forward and backward)
+    out = {}
+    for name, shape, sigma, seed in [("v2d", (128, 128), 8.0, 51), ("v3d", (16, 20, 24), 4.0, 52),
+                                     ("v2d_tiny", (128, 128), 1e-3, 53)]:
+        nd = len(shape)
+        vec = t(gi.smooth_field(gi.rng(seed), (2, nd, *shape), sigma)).requires_grad_()
+        gout = t(gi.weights(seed + 2, (2, nd, *shape), 1.0))
+        y = rl.VecInt(shape, 7)(vec)
+        y.backward(gout)
+        out[name + "/out"] = y.detach().numpy()
+        out[name + "/d_vec"] = vec.grad.numpy()
+        yn = rl.VecInt(shape, 7)(-vec.detach())
+        out[name + "/out_neg"] = yn.numpy()
+    for name, shape, seed in [("r2d", (64, 96), 61), ("r3d", (16, 20, 24), 62), ("r2d_odd", (37, 53), 63)]:
+        nd = len(shape)
+        x = t(gi.weights(seed, (2, nd, *shape), 1.0)).requires_grad_()
+        down = rl.ResizeTransform(2, nd)(x)
+        gd = t(gi.weights(seed + 1, tuple(down.shape), 1.0))
+        down.backward(gd)
+        out[name + "/down"] = down.detach().numpy()
+        out[name + "/down_dx"] = x.grad.numpy().copy()
+        x.grad = None
+        up = rl.ResizeTransform(0.5, nd)(x)
+        gu = t(gi.weights(seed + 2, tuple(up.shape), 1.0))
+        up.backward(gu)
+        out[name + "/up"] = up.detach().numpy()
+        out[name + "/up_dx"] = x.grad.numpy().copy()
+    save("vecint_resize", **out)
+
+    # ---- losses
+    out = {}
+    for name, shape, seed in [("n2d", (64, 64), 71), ("n3d", (24, 28, 32), 72), ("n2d_odd", (45, 70), 73)]:
+        nd = len(shape)
+        I = t(gi.image(seed, 2, shape)).requires_grad_()
+        J = t(gi.image(seed + 1, 2, shape)).requires_grad_()
+        crit = NCC_Loss('cpu', kernel_var=[9] * nd, kernel_type='mean')
+        loss = crit(I, J)
+        loss.backward()
+        out[name + "/loss"] = loss.detach().numpy()
+        out[name + "/cc"] = crit.ncc(I, J).detach().numpy()
+        out[name + "/dI"] = I.grad.numpy().copy()
+        out[name + "/dJ"] = J.grad.numpy().copy()
+        I.grad = None; J.grad = None
+        mask = t((gi.image(seed + 2, 2, shape) > -0.5).astype(np.float32))
+        lm = crit(I, J, mask=mask)
+        lm.backward()
+        out[name + "/loss_masked"] = lm.detach().numpy()
+        out[name + "/dI_masked"] = I.grad.numpy().copy()
+        out[name + "/loss_self"] = crit(I.detach(), I.detach()).numpy()
+    # survey known answers: NCC of rand/rand 2x1x64^2 under torch seed 1234
+    torch.manual_seed(1234)
+    a, b = torch.rand(2, 1, 64, 64), torch.rand(2, 1, 64, 64)
+    out["survey/ncc_rand_a"] = a.numpy(); out["survey/ncc_rand_b"] = b.numpy()
+    out["survey/ncc_rand"] = NCC_Loss('cpu', kernel_var=[9, 9])(a, b).numpy()
+    g = torch.randn(1, 3, 32, 32, 32)
+    out["survey/grad_in"] = g.numpy()
+    out["survey/grad_l2_3d"] = Grad_Loss(dim=3, penalty='l2')(g).numpy()
+
+    for name, shape, seed in [("g2d", (64, 80), 81), ("g3d", (12, 16, 20), 82)]:
+        nd = len(shape)
+        for pen in ("l1", "l2"):
+            x = t(gi.weights(seed, (2, nd, *shape), 1.0)).requires_grad_()
+            loss = Grad_Loss(dim=nd, penalty=pen, loss_mult=2 if pen == "l1" else None)(x)
+            loss.backward()
+            out[f"{name}/{pen}"] = loss.detach().numpy()
+            out[f"{name}/{pen}_dx"] = x.grad.numpy()
+    x = t(gi.weights(91, (2, 2, 64, 80), 1.0)).requires_grad_()
+    loss = smooothing_loss(x)
+    loss.backward()
+    out["smooth/loss"] = loss.detach().numpy(); out["smooth/dx"] = x.grad.numpy()
+
+    l1 = REGISTRATIONModel.calculate_L1_loss
+    a = t(gi.image(101, 2, (64, 64))).requires_grad_()
+    b = t(gi.image(102, 2, (64, 64))).requires_grad_()
+    mask = (b > -0.95) + (a > -0.95)
+    loss = l1(None, a, b, mask)
+    loss.backward()
+    out["l1/loss"] = loss.detach().numpy(); out["l1/da"] = a.grad.numpy(); out["l1/db"] = b.grad.numpy()
+    out["l1/mask_sum"] = mask.sum().numpy()
+    out["l1/empty"] = np.array(float(l1(None, a.detach(), b.detach(), torch.zeros_like(mask))))
+    out["l1/nomask"] = l1(None, a.detach(), b.detach(), None).numpy()
+    save("losses", **out)
+
+
+SECTIONS = {"ops": gen_ops}
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    todo = sys.argv[1:] or list(SECTIONS)
+    for s in todo:
+        print(f"[gen_golden] {s}")
+        SECTIONS[s]()

@@ -1,0 +1,77 @@
+"""Deterministic synthetic inputs shared by oracle/gen_golden.py (which runs the reference on them)
+and by the tests (which regenerate them instead of storing them).  numpy's legacy RandomState
+streams are stable across numpy versions, so only the reference OUTPUTS are committed."""
+import numpy as np
+
+
+def rng(seed):
+    return np.random.RandomState(seed)
+
+
+def smooth_field(r, shape, sigma_vox, smooth=4):
+    """Random field with amplitude ~sigma_vox, box-smoothed `smooth` times along every axis."""
+    x = r.standard_normal(shape).astype(np.float32)
+    for _ in range(smooth):
+        for ax in range(2, x.ndim):
+            x = (np.roll(x, 1, ax) + x + np.roll(x, -1, ax)) / 3.0
+    x = x / (x.std() + 1e-12) * sigma_vox
+    return x.astype(np.float32)
+
+
+def flow(seed, B, shape, sigma):
+    """Displacement field (B, nd, *shape). sigma = 0 gives exact zeros; small sigmas exercise the
+    floor/round decisions at integer coordinates."""
+    nd = len(shape)
+    if sigma == 0:
+        return np.zeros((B, nd, *shape), np.float32)
+    return (rng(seed).standard_normal((B, nd, *shape)) * sigma).astype(np.float32)
+
+
+def half_integer_flow(seed, B, shape):
+    """Adversarial: lands on half-integers +- k*2^-20 so round-half-even decisions matter."""
+    r = rng(seed)
+    nd = len(shape)
+    k = r.randint(-4, 5, size=(B, nd, *shape)).astype(np.float32)
+    base = r.randint(-3, 4, size=(B, nd, *shape)).astype(np.float32) + 0.5
+    return (base + k * np.float32(2.0 ** -20)).astype(np.float32)
+
+
+def image(seed, B, shape, C=1):
+    """Blob image in [-1, 1] with an exact -1 background outside a centred ellipsoid."""
+    r = rng(seed)
+    x = smooth_field(r, (B, C, *shape), 1.0, smooth=6)
+    x = np.tanh(3.0 * x).astype(np.float32)
+    grids = np.meshgrid(*[np.linspace(-1, 1, s, dtype=np.float32) for s in shape], indexing="ij")
+    rad = sum(g * g for g in grids)
+    x = np.where(rad[None, None] < 0.8, x, np.float32(-1.0)).astype(np.float32)
+    return x
+
+
+def index_ramps(B, shape):
+    """src whose channel d holds its own index along spatial axis d (observes sampled indices)."""
+    nd = len(shape)
+    g = np.stack(np.meshgrid(*[np.arange(s, dtype=np.float32) for s in shape], indexing="ij"))
+    return np.broadcast_to(g[None], (B, nd, *shape)).astype(np.float32).copy()
+
+
+def weights(seed, shape, scale):
+    return (rng(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+# (name, nd-shape, sigma, seed) warp cases; sizes follow SURVEY.md 3.5 / 8d
+WARP_CASES = [
+    ("w2d_256_s0", (256, 256), 0.0, 11),
+    ("w2d_256_s1e-5", (256, 256), 1e-5, 12),
+    ("w2d_256_s0.5", (256, 256), 0.5, 13),
+    ("w2d_256_s3", (256, 256), 3.0, 14),
+    ("w2d_256_s20", (256, 256), 20.0, 15),
+    ("w2d_128_s0", (128, 128), 0.0, 16),
+    ("w2d_160x192_s3", (160, 192), 3.0, 17),
+    ("w2d_37x53_s2", (37, 53), 2.0, 18),
+    ("w3d_32x40x48_s0", (32, 40, 48), 0.0, 21),
+    ("w3d_32x40x48_s1e-5", (32, 40, 48), 1e-5, 22),
+    ("w3d_32x40x48_s3", (32, 40, 48), 3.0, 23),
+    ("w3d_64_s0", (64, 64, 64), 0.0, 24),
+    ("w3d_17x19x23_s20", (17, 19, 23), 20.0, 25),
+]
+HALF_CASES = [("h2d_128", (128, 128), 31), ("h3d_24x28x32", (24, 28, 32), 32)]
