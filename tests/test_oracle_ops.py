@@ -114,8 +114,10 @@ def test_ncc_survey_known_answers(golden, orc):
 
 def test_ncc_constant_image_eps_path(orc):
     I = np.full((1, 1, 32, 32), 0.37, np.float32)
-    out = orc.ncc(I, I)
-    assert np.isfinite(out[0]) and -1e-2 <= out[0] <= 0.0   # I_var ~ 0 -> cc ~ cross^2/eps ~ 0
+    out, cc = orc.ncc(I, I, return_cc=True)
+    assert np.isfinite(out[0]) and -1.0 <= out[0] <= 0.0
+    assert np.all(cc[..., 4:-4, 4:-4] < 1e-2)   # interior: I_var ~ 0 -> cc = cross^2/eps ~ 0
+    assert np.all(cc[..., 0, :] > 0.9)          # border windows see the zero padding: cc ~ 1
 
 
 @pytest.mark.parametrize("name,shape,seed", [("g2d", (64, 80), 81), ("g3d", (12, 16, 20), 82)])
