@@ -128,8 +128,8 @@ def gen_ops():
     out = {}
     for name, shape, seed in [("n2d", (64, 64), 71), ("n3d", (24, 28, 32), 72), ("n2d_odd", (45, 70), 73)]:
         nd = len(shape)
-        I = t(gi.image(seed, 2, shape)).requires_grad_()
-        J = t(gi.image(seed + 1, 2, shape)).requires_grad_()
+        I = t(gi.image_textured(seed, 2, shape)).requires_grad_()
+        J = t(gi.image_textured(seed + 1, 2, shape)).requires_grad_()
         crit = NCC_Loss('cpu', kernel_var=[9] * nd, kernel_type='mean')
         loss = crit(I, J)
         loss.backward()

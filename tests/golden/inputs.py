@@ -47,6 +47,17 @@ def image(seed, B, shape, C=1):
     return x
 
 
+def image_textured(seed, B, shape, C=1, amp=0.05, flat_bg=True):
+    """image() plus a fine texture inside the ellipsoid (background stays exactly -1 on the same support
+    for every seed).  Every 9^nd window that is not exactly flat then has a variance far above the fp32
+    cancellation noise of the reference's NCC formula (S2 - 2*u*S + u*u*W, eps 1e-5), which is
+    otherwise chaotic wherever one image is nearly (not exactly) constant: see DESIGN.md "NCC conditioning"."""
+    x = image(seed, B, shape, C)
+    t = (rng(seed + 7919).standard_normal(x.shape) * amp).astype(np.float32)
+    y = np.clip(x * np.float32(0.9) + t, -0.94, 1.0).astype(np.float32)
+    return np.where(x == np.float32(-1.0), x, y).astype(np.float32) if flat_bg else y
+
+
 def index_ramps(B, shape):
     """src whose channel d holds its own index along spatial axis d (observes sampled indices)."""
     nd = len(shape)

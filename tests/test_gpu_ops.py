@@ -127,8 +127,8 @@ def test_resize(name, shape, seed, golden, L):
 def test_ncc(name, shape, seed, golden, orc, LS):
     g = golden("losses")
     nd = len(shape)
-    I = cu(gi.image(seed, 2, shape)).requires_grad_()
-    J = cu(gi.image(seed + 1, 2, shape)).requires_grad_()
+    I = cu(gi.image_textured(seed, 2, shape)).requires_grad_()
+    J = cu(gi.image_textured(seed + 1, 2, shape)).requires_grad_()
     crit = LS.NCC_Loss('cuda', kernel_var=[9] * nd, kernel_type='mean')
     loss = crit(I, J)
     assert abs(loss.item() - float(g[name + "/loss"])) <= 1e-4      # north_star: fp32 NCC within 1e-4

@@ -93,7 +93,7 @@ def test_resize(name, shape, seed, golden, orc):
 @pytest.mark.parametrize("name,shape,seed", [("n2d", (64, 64), 71), ("n3d", (24, 28, 32), 72), ("n2d_odd", (45, 70), 73)])
 def test_ncc(name, shape, seed, golden, orc):
     g = golden("losses")
-    I, J = gi.image(seed, 2, shape), gi.image(seed + 1, 2, shape)
+    I, J = gi.image_textured(seed, 2, shape), gi.image_textured(seed + 1, 2, shape)
     out, cc = orc.ncc(I, J, return_cc=True)
     assert abs(out[0] - g[name + "/loss"]) <= 1e-4          # the north_star tolerance
     np.testing.assert_allclose(cc, g[name + "/cc"], atol=2e-3, rtol=1e-3)
