@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py — volume-pairs/sec (fwd+bwd+Adam) of the DFMIR translation+registration training step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
+
+Workload (BASELINE.json configs[1]): 2-D 256x256, batch 16 MR->CT pairs per GPU, one full
+REGISTRATIONModel.optimize_parameters (ResnetGenerator-9blocks x (2 full + 6 encoder passes),
+VoxelMorph-2D + VecInt, PatchNCE x3, masked L1 x2, smoothing, backward, 3 Adam steps), synthetic
+images, random-initialised weights.  One process per GPU (torchrun for N > 1, NCCL gradient
+all-reduce); weak scaling (per-GPU batch fixed).  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the reference's CPU PyTorch path (oracle/torch_port.py, pinned to the
+reference's own step by tests/test_oracle_nets.py) on the host cores, one pair per step.
+"""
+import argparse
+import contextlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "volume-pairs/sec (fwd+bwd)"
+UNIT = "pairs/s"
+
+
+def synthetic_pair(B, S, seed):
+    """Smooth blob images in [-1, 1] with an exact -1 background outside a centred ellipse."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, S), torch.linspace(-1, 1, S), indexing="ij")
+    inside = (xx * xx + yy * yy) < 0.8
+    for dom in range(2):
+        x = torch.randn(B, 1, S, S, generator=g)
+        k = torch.ones(1, 1, 9, 9) / 81.0
+        for _ in range(3):
+            x = torch.nn.functional.conv2d(x, k, padding=4)
+        x = torch.tanh(3.0 * x / x.std()) * 0.9 + 0.03 * torch.randn(B, 1, S, S, generator=g)
+        x = torch.where(inside[None, None], x.clamp(-0.94, 1.0), torch.full_like(x, -1.0))
+        out.append(x.contiguous())
+    return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    def __init__(self, dev):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(dev), "--query-gpu=clocks.sm,clocks.max.sm,power.draw,"
+                 "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        # median of the samples taken under load (upper half), as idle samples precede the region
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's CPU PyTorch path (oracle/torch_port.Step) on all host cores: one pair per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S = args.size
+    G, Fd, R = tp.random_state_dicts(crop=S)
+    A, B = synthetic_pair(1, S, 1234)
+    st = tp.Step(G, Fd, R, n_blocks=9, batch_size=1, dvf_image=torch.zeros(1, 3, S, S))
+    for _ in range(args.warmup):
+        st.step(A, B)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st.step(A, B)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} steps of 1 pair (batch 1) at {S}x{S}, torch CPU fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"2D {S}x{S} translation+registration fwd/bwd+Adam (BASELINE configs[1]); CPU sample: batch 1 per step",
+                   "batch_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(S, budget_s=25.0):
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    G, Fd, R = tp.random_state_dicts(crop=S)
+    A, B = synthetic_pair(1, S, 1234)
+    st = tp.Step(G, Fd, R, n_blocks=9, batch_size=1, dvf_image=torch.zeros(1, 3, S, S))
+    st.step(A, B)
+    n, t0 = 0, time.perf_counter()
+    while n < 2 or (time.perf_counter() - t0 < budget_s and n < 8):
+        st.step(A, B)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} steps of 1 pair (batch 1) at {S}x{S} after 1 warm-up, oracle/torch_port.py (torch CPU fp32, {cores} threads)"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from dfmir_b200 import _lib, registration_model as rm
+    from dfmir_b200 import functional as Fn
+
+    B, S = args.batch, args.size
+    opt = rm.default_options(batch_size=B, crop_size=S, load_size=S, gpu_ids=[local])
+    torch.manual_seed(1234)
+    with contextlib.redirect_stdout(sys.stderr):
+        model = rm.REGISTRATIONModel(opt)
+        A, Bm = synthetic_pair(B, S, 1234 + rank)
+        data = {"A": A.pin_memory(), "B": Bm.pin_memory()}
+        model.data_dependent_initialize(data)
+        model.setup(opt)
+        model.parallelize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    model.set_input(data)
+
+    def step_resident():
+        model.optimize_parameters()
+
+    def step_e2e():
+        model.set_input(data)
+        model.optimize_parameters()
+        model.get_current_losses()
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    prof = Fn.ConvProfile()
+    Fn.PROFILE = prof
+    _lib.launch_count_reset()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count()
+    Fn.PROFILE = None
+    conv_ms, conv_flops, conv_calls = prof.total()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    value = B * world * args.steps / (ms / 1e3)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    peak = pk["bf16_tflops_sustained"]
+    engine = Fn.CONV_ENGINE
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32" if prof.umma_calls else "f32", "data": "synthetic",
+        "config": {"workload": f"2D {S}x{S} batch={B}/GPU translation+registration fwd/bwd+Adam (BASELINE configs[1])",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "conv_engine": engine, "umma_conv_calls": prof.umma_calls, "simt_conv_calls": conv_calls - prof.umma_calls,
+                   "l2_policy": "inputs larger than L2: each step streams > 10 GB of activations (L2 is 126 MB)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(2 * B * S * S * 4), "d2h_bytes_per_step": 6 * 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "conv implicit-GEMM launches (fwd+dgrad+wgrad) of the step",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "peak_source": f"bf16_tflops_sustained, {pk_src} (TF32 dense peak is about half of it)",
+                     "flops_per_step": conv_flops / args.steps, "kernel_ms_per_step": conv_ms / args.steps,
+                     "share_of_step": conv_ms / ms if ms > 0 else None, "launches_per_step": conv_calls / args.steps,
+                     "traffic": None},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(S)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="pairs per GPU per step")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the dfmir_b200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

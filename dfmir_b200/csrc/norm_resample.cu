@@ -1,0 +1,493 @@
+// Memory-bound layers around the convolutions of the translation net and the registration U-Net,
+// channels-last fp32:
+//   InstanceNorm2d(affine=False) [+ ReLU] [+ residual add] [+ ReflectionPad2d of the result]
+//       models/networks.py:984,996,1020 (norm + ReLU), :1193-1214 (ResnetBlock: pad, norm, skip add :1220)
+//   ReflectionPad2d                     models/networks.py:982,1022
+//   Downsample (anti-aliased blur-pool) models/networks.py:37-60   (reflect pad 1, [1,2,1]^2/16, stride 2)
+//   Upsample   (anti-aliased blur-up)   models/networks.py:73-93   (replicate pad, conv_transpose [1,3,3,1]^2/16, crop)
+//   nn.Upsample(nearest x2) + torch.cat models/voxelmorph/torchvoxelmorph/networks.py:99-102
+// Each is one pass over HBM (stats: one read; apply: one read + one write); the normalised tensor
+// is written directly in the padded layout the next convolution's loader wants.
+#include "common.cuh"
+#include "dfmir_b200.h"
+
+namespace {
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // ReflectionPad: no edge repeat
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+inline int ew_grid(long long items) {
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)dfmir_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------ instance norm: statistics
+// sums[(n*C + c)*2 + {0,1}] += sum x, sum x^2 over a chunk of pixels (fp64 accumulation).
+__global__ void __launch_bounds__(256)
+in_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int HW, int C, int chunk) {
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+  const float* xb = x + (long long)n * HW * C;
+  // thread -> channel (fastest), pixel lane
+  const int cl = C < 256 ? C : 256;
+  const int c_lane = threadIdx.x % cl, p_lane = threadIdx.x / cl, pl = 256 / cl;
+  if (p_lane >= pl) return;
+  for (int c = c_lane; c < C; c += cl) {
+    double s = 0, ss = 0;
+    for (int p = p0 + p_lane; p < p1; p += pl) {
+      const float v = xb[(long long)p * C + c];
+      s += (double)v; ss += (double)v * (double)v;
+    }
+    atomicAdd(sums + ((long long)n * C + c) * 2, s);
+    atomicAdd(sums + ((long long)n * C + c) * 2 + 1, ss);
+  }
+}
+
+// stats[(n*C + c)*2] = mean, [..+1] = 1/sqrt(var + eps)  (biased variance, as F.instance_norm)
+__global__ void in_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, int NC, int HW,
+                                   float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  const double m = sums[2 * i] / HW;
+  double var = sums[2 * i + 1] / HW - m * m;
+  if (var < 0) var = 0;
+  stats[2 * i] = (float)m;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// y[n, hp, wp, c] = act((x[n,h,w,c] - mean) * rstd) (+ res[n, h+rp, w+rp, c]); (h,w) = reflect(hp-p, wp-p)
+__global__ void __launch_bounds__(256)
+in_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ res,
+                float* __restrict__ y, int N, int H, int W, int C, int relu, int p, int rp) {
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  const long long total = (long long)N * HP * WP * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int wp = (int)(q % WP); q /= WP;
+    const int hp = (int)(q % HP); q /= HP;
+    const int n = (int)q;
+    const int h = reflect_idx(hp - p, H), w = reflect_idx(wp - p, W);
+    const float mean = __ldg(stats + ((long long)n * C + c) * 2), rstd = __ldg(stats + ((long long)n * C + c) * 2 + 1);
+    float v = (x[(((long long)n * H + h) * W + w) * C + c] - mean) * rstd;
+    if (relu) v = v > 0.f ? v : 0.f;
+    if (res) v += res[(((long long)n * (H + 2 * rp) + h + rp) * (W + 2 * rp) + w + rp) * C + c];
+    y[i] = v;
+  }
+}
+
+// Sum of the padded-gradient entries that alias interior pixel (h,w): the adjoint of reflect_idx.
+__device__ __forceinline__ int fold_list(int h, int H, int p, int* out) {
+  int n = 0;
+  out[n++] = h + p;
+  if (p > 0) {
+    if (h >= 1 && h <= p) out[n++] = p - h;
+    if (h <= H - 2 && h >= H - 1 - p) out[n++] = 2 * (H - 1) - h + p;
+  }
+  return n;
+}
+
+// pass 1: g = fold(dy) (* relu mask); store g in dx (and in the interior of dres); accumulate
+// sum g, sum g*xhat per (n,c).
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ stats,
+                     float* __restrict__ dx, float* __restrict__ dres, double* __restrict__ sums, int H, int W, int C,
+                     int relu, int p, int rp, int chunk) {
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  const int cl = C < 256 ? C : 256;
+  const int c_lane = threadIdx.x % cl, p_lane = threadIdx.x / cl, pl = 256 / cl;
+  if (p_lane >= pl) return;
+  for (int c = c_lane; c < C; c += cl) {
+    const float mean = stats[((long long)n * C + c) * 2], rstd = stats[((long long)n * C + c) * 2 + 1];
+    double s1 = 0, s2 = 0;
+    for (int px = p0 + p_lane; px < p1; px += pl) {
+      const int h = px / W, w = px - h * W;
+      int hl[3], wl[3];
+      const int nh = fold_list(h, H, p, hl), nw = fold_list(w, W, p, wl);
+      float g = 0.f;
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b) g += dy[(((long long)n * HP + hl[a]) * WP + wl[b]) * C + c];
+      const long long o = ((long long)n * HW + px) * C + c;
+      if (dres) dres[(((long long)n * (H + 2 * rp) + h + rp) * (W + 2 * rp) + w + rp) * C + c] = g;
+      const float xh = (x[o] - mean) * rstd;
+      if (relu && !(xh > 0.f)) g = 0.f;
+      dx[o] = g;
+      s1 += (double)g; s2 += (double)g * (double)xh;
+    }
+    atomicAdd(sums + ((long long)n * C + c) * 2, s1);
+    atomicAdd(sums + ((long long)n * C + c) * 2 + 1, s2);
+  }
+}
+
+// pass 2: dx = rstd * (g - mean(g) - xhat * mean(g * xhat))
+__global__ void __launch_bounds__(256)
+in_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, const double* __restrict__ sums,
+                    float* __restrict__ dx, int N, int HW, int C) {
+  const long long total = (long long)N * HW * C;
+  const double inv = 1.0 / HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int n = (int)(i / ((long long)HW * C));
+    const long long sc = ((long long)n * C + c) * 2;
+    const float mean = __ldg(stats + sc), rstd = __ldg(stats + sc + 1);
+    const float m1 = (float)(sums[sc] * inv), m2 = (float)(sums[sc + 1] * inv);
+    const float xh = (x[i] - mean) * rstd;
+    dx[i] = rstd * (dx[i] - m1 - xh * m2);
+  }
+}
+
+// ------------------------------------------------------------------ reflection pad (stand-alone)
+__global__ void __launch_bounds__(256)
+pad_reflect_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int p) {
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  const long long total = (long long)N * HP * WP * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int wp = (int)(q % WP); q /= WP;
+    const int hp = (int)(q % HP); q /= HP;
+    const int n = (int)q;
+    y[i] = x[(((long long)n * H + reflect_idx(hp - p, H)) * W + reflect_idx(wp - p, W)) * C + c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pad_reflect_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int p) {
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  const long long total = (long long)N * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int w = (int)(q % W); q /= W;
+    const int h = (int)(q % H); q /= H;
+    const int n = (int)q;
+    int hl[3], wl[3];
+    const int nh = fold_list(h, H, p, hl), nw = fold_list(w, W, p, wl);
+    float g = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) g += dy[(((long long)n * HP + hl[a]) * WP + wl[b]) * C + c];
+    dx[i] = g;
+  }
+}
+
+// ------------------------------------------------------------------ blur-pool down (x0.5)
+__global__ void __launch_bounds__(256)
+blur_down_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int OH, int OW) {
+  const long long total = (long long)N * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int ow = (int)(q % OW); q /= OW;
+    const int oh = (int)(q % OH); q /= OH;
+    const int n = (int)q;
+    const float* xb = x + (long long)n * H * W * C + c;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int h = reflect_idx(2 * oh - 1 + a, H);
+      const float fa = a == 1 ? 0.5f : 0.25f;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int w = reflect_idx(2 * ow - 1 + b, W);
+        const float fb = b == 1 ? 0.5f : 0.25f;
+        acc += xb[((long long)h * W + w) * C] * (fa * fb);
+      }
+    }
+    y[i] = acc;
+  }
+}
+
+// adjoint taps of the blur-pool along one axis: list of (o, weight) that read input index h
+__device__ __forceinline__ int blur_down_adj(int h, int H, int OH, int* o, float* wt) {
+  int n = 0;
+  int cand[3]; int nc = 0;
+  cand[nc++] = h;
+  if (h == 1) cand[nc++] = -1;
+  if (h == H - 2) cand[nc++] = H;
+  for (int k = 0; k < nc; ++k) {
+    const int hp = cand[k];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int num = hp + 1 - a;
+      if (num < 0 || (num & 1)) continue;
+      const int oo = num >> 1;
+      if (oo >= OH) continue;
+      o[n] = oo; wt[n] = a == 1 ? 0.5f : 0.25f; ++n;
+    }
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(256)
+blur_down_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
+  const long long total = (long long)N * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int w = (int)(q % W); q /= W;
+    const int h = (int)(q % H); q /= H;
+    const int n = (int)q;
+    int oh[6], ow[6]; float fh[6], fw[6];
+    const int nh = blur_down_adj(h, H, OH, oh, fh), nw = blur_down_adj(w, W, OW, ow, fw);
+    const float* gb = dy + (long long)n * OH * OW * C + c;
+    float acc = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) acc += gb[((long long)oh[a] * OW + ow[b]) * C] * (fh[a] * fw[b]);
+    dx[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ blur-up (x2)
+// per axis: y[2m] = (x[clamp(m-1)] + 3 x[m]) / 4 ; y[2m+1] = (3 x[m] + x[clamp(m+1)]) / 4
+__global__ void __launch_bounds__(256)
+blur_up_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)N * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int ow = (int)(q % OW); q /= OW;
+    const int oh = (int)(q % OH); q /= OH;
+    const int n = (int)q;
+    const int mh = oh >> 1, mw = ow >> 1;
+    const int h0 = (oh & 1) ? mh : max(mh - 1, 0), h1 = (oh & 1) ? min(mh + 1, H - 1) : mh;
+    const int w0 = (ow & 1) ? mw : max(mw - 1, 0), w1 = (ow & 1) ? min(mw + 1, W - 1) : mw;
+    const float fh0 = (oh & 1) ? 0.75f : 0.25f, fh1 = 1.f - fh0;
+    const float fw0 = (ow & 1) ? 0.75f : 0.25f, fw1 = 1.f - fw0;
+    const float* xb = x + (long long)n * H * W * C + c;
+    y[i] = fh0 * (fw0 * xb[((long long)h0 * W + w0) * C] + fw1 * xb[((long long)h0 * W + w1) * C]) +
+           fh1 * (fw0 * xb[((long long)h1 * W + w0) * C] + fw1 * xb[((long long)h1 * W + w1) * C]);
+  }
+}
+
+__device__ __forceinline__ int blur_up_adj(int m, int H, int* o, float* wt) {
+  int n = 0;
+  o[n] = 2 * m; wt[n++] = 0.75f;
+  o[n] = 2 * m + 1; wt[n++] = 0.75f;
+  if (m + 1 <= H - 1) { o[n] = 2 * m + 2; wt[n++] = 0.25f; } else { o[n] = 2 * m + 1; wt[n++] = 0.25f; }  // clamp(m+1)
+  if (m - 1 >= 0) { o[n] = 2 * m - 1; wt[n++] = 0.25f; } else { o[n] = 2 * m; wt[n++] = 0.25f; }          // clamp(m-1)
+  return n;
+}
+
+__global__ void __launch_bounds__(256)
+blur_up_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C) {
+  const int OW = 2 * W, OH = 2 * H;
+  const long long total = (long long)N * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int w = (int)(q % W); q /= W;
+    const int h = (int)(q % H); q /= H;
+    const int n = (int)q;
+    int oh[4], ow[4]; float fh[4], fw[4];
+    const int nh = blur_up_adj(h, H, oh, fh), nw = blur_up_adj(w, W, ow, fw);
+    const float* gb = dy + (long long)n * OH * OW * C + c;
+    float acc = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) acc += gb[((long long)oh[a] * OW + ow[b]) * C] * (fh[a] * fw[b]);
+    dx[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ nearest x2 upsample + concat (U-Net skip)
+struct UcGeom { int N, nd, C1, C2; int S[3]; };  // S = full-resolution spatial dims (right-aligned)
+
+__global__ void __launch_bounds__(256)
+upcat_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, UcGeom g) {
+  const int C = g.C1 + g.C2;
+  const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
+  const long long total = (long long)g.N * vox * C;
+  const int L0 = g.S[0] > 1 ? g.S[0] / 2 : 1, L1 = g.S[1] / 2, L2 = g.S[2] / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % C); q /= C;
+    const int xw = (int)(q % g.S[2]); q /= g.S[2];
+    const int yh = (int)(q % g.S[1]); q /= g.S[1];
+    const int zd = (int)(q % g.S[0]); q /= g.S[0];
+    const int n = (int)q;
+    float v;
+    if (c < g.C1) {
+      const int lz = g.S[0] > 1 ? zd >> 1 : 0;
+      v = a[((((long long)n * L0 + lz) * L1 + (yh >> 1)) * L2 + (xw >> 1)) * g.C1 + c];
+    } else {
+      v = b[((((long long)n * g.S[0] + zd) * g.S[1] + yh) * g.S[2] + xw) * g.C2 + (c - g.C1)];
+    }
+    y[i] = v;
+  }
+}
+
+// da = sum over the 2^nd children of dy[..., :C1];  db = dy[..., C1:]
+__global__ void __launch_bounds__(256)
+upcat_bwd_kernel(const float* __restrict__ dy, float* __restrict__ da, float* __restrict__ db, UcGeom g) {
+  const int C = g.C1 + g.C2;
+  const int L0 = g.S[0] > 1 ? g.S[0] / 2 : 1, L1 = g.S[1] / 2, L2 = g.S[2] / 2;
+  const long long na = (long long)g.N * L0 * L1 * L2 * g.C1;
+  const long long nb = (long long)g.N * g.S[0] * g.S[1] * g.S[2] * g.C2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (long long)gridDim.x * blockDim.x) {
+    if (i < na) {
+      long long q = i;
+      const int c = (int)(q % g.C1); q /= g.C1;
+      const int lx = (int)(q % L2); q /= L2;
+      const int ly = (int)(q % L1); q /= L1;
+      const int lz = (int)(q % L0); q /= L0;
+      const int n = (int)q;
+      float acc = 0.f;
+      const int nz = g.S[0] > 1 ? 2 : 1;
+      for (int dz = 0; dz < nz; ++dz)
+        for (int dyy = 0; dyy < 2; ++dyy)
+          for (int dxx = 0; dxx < 2; ++dxx) {
+            const int zd = g.S[0] > 1 ? 2 * lz + dz : 0;
+            acc += dy[((((long long)n * g.S[0] + zd) * g.S[1] + 2 * ly + dyy) * g.S[2] + 2 * lx + dxx) * C + c];
+          }
+      if (da) da[i] = acc;
+    } else if (db) {
+      const long long j = i - na;
+      const int c = (int)(j % g.C2);
+      const long long pos = j / g.C2;
+      db[j] = dy[pos * C + g.C1 + c];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" size_t dfmir_instnorm_workspace_bytes(int N, int C) { return sizeof(double) * 2 * (size_t)N * C + 256; }
+
+static int in_chunk(int HW, int N, int* nchunks) {
+  // enough CTAs for ~4 per SM, at least 256 pixels per CTA
+  int want = (4 * dfmir_num_sms() + N - 1) / N;
+  int chunk = (HW + want - 1) / want;
+  if (chunk < 256) chunk = 256;
+  *nchunks = (HW + chunk - 1) / chunk;
+  return chunk;
+}
+
+extern "C" int dfmir_instnorm_fwd(const float* x, const float* res, float* y, float* stats, void* ws, size_t ws_bytes,
+                                  int N, int H, int W, int C, float eps, int relu, int out_pad, int res_pad,
+                                  void* stream) {
+  DFMIR_CHECK_ARG(x && y && stats && ws, "dfmir_instnorm_fwd: null pointer");
+  DFMIR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0, "dfmir_instnorm_fwd: bad sizes");
+  DFMIR_CHECK_ARG(out_pad >= 0 && out_pad < H && out_pad < W && res_pad >= 0, "dfmir_instnorm_fwd: bad padding");
+  DFMIR_CHECK_ARG(ws_bytes >= dfmir_instnorm_workspace_bytes(N, C), "dfmir_instnorm_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sums = (double*)ws;
+  DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  int nch; const int chunk = in_chunk(H * W, N, &nch);
+  in_stats_kernel<<<dim3(nch, N), 256, 0, st>>>(x, sums, H * W, C, chunk);
+  DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(stats)");
+  in_finalize_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, stats, N * C, H * W, eps);
+  DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(finalize)");
+  const long long total = (long long)N * (H + 2 * out_pad) * (W + 2 * out_pad) * C;
+  in_apply_kernel<<<ew_grid(total), 256, 0, st>>>(x, stats, res, y, N, H, W, C, relu, out_pad, res_pad);
+  DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(apply)");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_instnorm_bwd(const float* dy, const float* x, const float* stats, float* dx, float* dres,
+                                  void* ws, size_t ws_bytes, int N, int H, int W, int C, int relu, int out_pad,
+                                  int res_pad, void* stream) {
+  DFMIR_CHECK_ARG(dy && x && stats && dx && ws, "dfmir_instnorm_bwd: null pointer");
+  DFMIR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0, "dfmir_instnorm_bwd: bad sizes");
+  DFMIR_CHECK_ARG(ws_bytes >= dfmir_instnorm_workspace_bytes(N, C), "dfmir_instnorm_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* sums = (double*)ws;
+  DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  if (dres && res_pad > 0)
+    DFMIR_CUDA(cudaMemsetAsync(dres, 0, sizeof(float) * (size_t)N * (H + 2 * res_pad) * (W + 2 * res_pad) * C, st));
+  int nch; const int chunk = in_chunk(H * W, N, &nch);
+  in_bwd_reduce_kernel<<<dim3(nch, N), 256, 0, st>>>(dy, x, stats, dx, dres, sums, H, W, C, relu, out_pad, res_pad, chunk);
+  DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(reduce)");
+  in_bwd_apply_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, st>>>(x, stats, sums, dx, N, H * W, C);
+  DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(apply)");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_pad_reflect_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, void* stream) {
+  DFMIR_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "dfmir_pad_reflect_fwd: bad argument");
+  DFMIR_CHECK_ARG(pad >= 0 && pad < H && pad < W, "dfmir_pad_reflect_fwd: pad %d must be smaller than the image", pad);
+  const long long total = (long long)N * (H + 2 * pad) * (W + 2 * pad) * C;
+  pad_reflect_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C, pad);
+  DFMIR_CHECK_LAUNCH("dfmir_pad_reflect_fwd");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_pad_reflect_bwd(const float* dy, float* dx, int N, int H, int W, int C, int pad, void* stream) {
+  DFMIR_CHECK_ARG(dy && dx && N > 0 && H > 0 && W > 0 && C > 0, "dfmir_pad_reflect_bwd: bad argument");
+  DFMIR_CHECK_ARG(pad >= 0 && pad < H && pad < W, "dfmir_pad_reflect_bwd: pad %d must be smaller than the image", pad);
+  pad_reflect_bwd_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C, pad);
+  DFMIR_CHECK_LAUNCH("dfmir_pad_reflect_bwd");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_blur_down_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  DFMIR_CHECK_ARG(x && y && N > 0 && H > 1 && W > 1 && C > 0, "dfmir_blur_down_fwd: bad argument");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  blur_down_fwd_kernel<<<ew_grid((long long)N * OH * OW * C), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C, OH, OW);
+  DFMIR_CHECK_LAUNCH("dfmir_blur_down_fwd");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_blur_down_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
+  DFMIR_CHECK_ARG(dy && dx && N > 0 && H > 1 && W > 1 && C > 0, "dfmir_blur_down_bwd: bad argument");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  blur_down_bwd_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C, OH, OW);
+  DFMIR_CHECK_LAUNCH("dfmir_blur_down_bwd");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_blur_up_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
+  DFMIR_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "dfmir_blur_up_fwd: bad argument");
+  blur_up_fwd_kernel<<<ew_grid((long long)N * 4 * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C);
+  DFMIR_CHECK_LAUNCH("dfmir_blur_up_fwd");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_blur_up_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
+  DFMIR_CHECK_ARG(dy && dx && N > 0 && H > 0 && W > 0 && C > 0, "dfmir_blur_up_bwd: bad argument");
+  blur_up_bwd_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C);
+  DFMIR_CHECK_LAUNCH("dfmir_blur_up_bwd");
+  return DFMIR_OK;
+}
+
+static int make_uc(UcGeom& g, int N, int nd, const int* shape, int C1, int C2) {
+  if ((nd != 2 && nd != 3) || N < 1 || C1 < 1 || C2 < 0) return -1;
+  g.N = N; g.nd = nd; g.C1 = C1; g.C2 = C2;
+  g.S[0] = 1;
+  for (int a = 0; a < nd; ++a) {
+    g.S[a + 3 - nd] = shape[a];
+    if (shape[a] < 2 || (shape[a] & 1)) return -1;  // x2 nearest upsample: full-res dims are even
+  }
+  return 0;
+}
+
+extern "C" int dfmir_upsample_concat_fwd(const float* a, const float* b, float* y, int N, int nd, const int* shape,
+                                         int C1, int C2, void* stream) {
+  UcGeom g;
+  DFMIR_CHECK_ARG(make_uc(g, N, nd, shape, C1, C2) == 0, "dfmir_upsample_concat_fwd: bad geometry (even full-res dims, nd 2|3)");
+  DFMIR_CHECK_ARG(a && y && (b || C2 == 0), "dfmir_upsample_concat_fwd: null pointer");
+  const long long total = (long long)N * g.S[0] * g.S[1] * g.S[2] * (C1 + C2);
+  upcat_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(a, b, y, g);
+  DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_fwd");
+  return DFMIR_OK;
+}
+
+extern "C" int dfmir_upsample_concat_bwd(const float* dy, float* da, float* db, int N, int nd, const int* shape,
+                                         int C1, int C2, void* stream) {
+  UcGeom g;
+  DFMIR_CHECK_ARG(make_uc(g, N, nd, shape, C1, C2) == 0, "dfmir_upsample_concat_bwd: bad geometry");
+  DFMIR_CHECK_ARG(dy && (da || db), "dfmir_upsample_concat_bwd: null pointer");
+  const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
+  const long long total = (long long)N * (vox >> nd) * C1 + (long long)N * vox * C2;
+  upcat_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dy, da, db, g);
+  DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_bwd");
+  return DFMIR_OK;
+}

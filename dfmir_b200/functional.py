@@ -1,0 +1,448 @@
+"""autograd bindings of the convolution / normalisation / resampling / PatchNCE entry points of
+libdfmir_b200.so (include/dfmir_b200.h).  torch supplies device memory, streams and the autograd
+tape; every forward and backward below is a C-ABI call into hand-written sm_100a kernels.
+
+Internal activation layout is channels-last: (N, *spatial, C) contiguous fp32.
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_LEAKY, ACT_TANH, ACT_RELU = 0, 1, 2, 3
+
+# convolution engine: "simt" = fp32 CUDA cores (exact), "umma" = tcgen05 tensor cores (TF32 operands)
+# for the layer shapes it supports, "auto" = umma where supported.
+CONV_ENGINE = os.environ.get("DFMIR_CONV_ENGINE", "auto")
+
+
+class ConvProfile:
+    """bench.py instrumentation: CUDA-event pairs around every convolution launch on the launching
+    stream, with the algorithmic FLOPs (2*M*N*K) of each call."""
+
+    def __init__(self):
+        self.events, self.flops, self.calls, self.umma_calls = [], 0.0, 0, 0
+
+    def run(self, fn, flops, umma=False):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        self.events.append((s, e))
+        self.flops += flops
+        self.calls += 1
+        self.umma_calls += int(umma)
+
+    def total(self):
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in self.events), self.flops, self.calls
+
+
+PROFILE = None
+
+
+def _run(fn, flops, umma=False):
+    if PROFILE is None:
+        fn()
+    else:
+        PROFILE.run(fn, flops, umma)
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("nd", ctypes.c_int), ("N", ctypes.c_int), ("Cin", ctypes.c_int), ("Cout", ctypes.c_int),
+                ("in_shape", ctypes.c_int * 3), ("out_shape", ctypes.c_int * 3), ("kernel", ctypes.c_int * 3),
+                ("pad", ctypes.c_int * 3), ("stride", ctypes.c_int), ("act", ctypes.c_int),
+                ("x_strides", ctypes.c_longlong * 5), ("y_strides", ctypes.c_longlong * 5)]
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise _lib.DfmirError(f"dfmir_b200 kernels are fp32; got {t.dtype}")
+    return t
+
+
+def _cl_strides(t, nd, planar=False):
+    """element strides {n, spatial[nd], c} of a channels-last (N,*S,C) or planar (N,C,*S) tensor"""
+    st = t.stride()
+    if planar:
+        return [st[0]] + list(st[2:2 + nd]) + [st[1]]
+    return list(st[:nd + 2])
+
+
+def _make_desc(nd, N, Cin, Cout, in_shape, out_shape, kernel, pad, stride, act, xs, ys):
+    d = ConvDesc()
+    d.nd, d.N, d.Cin, d.Cout, d.stride, d.act = nd, N, Cin, Cout, stride, act
+    for i in range(nd):
+        d.in_shape[i], d.out_shape[i], d.kernel[i], d.pad[i] = in_shape[i], out_shape[i], kernel[i], pad[i]
+    for i in range(nd + 2):
+        d.x_strides[i], d.y_strides[i] = xs[i], ys[i]
+    return d
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _use_umma(desc_args):
+    if CONV_ENGINE == "simt":
+        return False
+    from . import umma
+    return umma.supported(*desc_args)
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = act(conv(x, w) + b); x (N,*S,Cin) channels-last (any strides), w (taps,Cin,Cout)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, kernel, stride, pad, act, planar_out):
+        _lib.require_cuda(x, w)
+        x, w = _f32(x), _f32(w).contiguous()
+        nd = len(kernel)
+        N, Cin = x.shape[0], x.shape[-1]
+        S = list(x.shape[1:1 + nd])
+        Cout = w.shape[2]
+        if w.shape[0] != math.prod(kernel) or w.shape[1] != Cin:
+            raise _lib.DfmirError(f"conv: weight {tuple(w.shape)} does not match kernel {kernel} / Cin {Cin}")
+        O = [(S[i] + 2 * pad[i] - kernel[i]) // stride + 1 for i in range(nd)]
+        if planar_out:
+            y = torch.empty((N, Cout, *O), dtype=x.dtype, device=x.device)
+        else:
+            y = torch.empty((N, *O, Cout), dtype=x.dtype, device=x.device)
+        d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, act, _cl_strides(x, nd), _cl_strides(y, nd, planar_out))
+        if bias is not None:
+            bias = _f32(bias).contiguous()
+        engine = "simt"
+        flops = 2.0 * N * math.prod(O) * Cout * w.shape[0] * Cin
+        if _use_umma((nd, Cin, Cout, kernel, stride, pad, x, planar_out)):
+            from . import umma
+            _run(lambda: umma.conv_fwd(x, w, bias, y, d), flops, True)
+            engine = "umma"
+        else:
+            _run(lambda: _lib.call("dfmir_conv_fwd", x, w, bias, y, ctypes.byref(d)), flops)
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        ctx.meta = (nd, N, Cin, Cout, S, O, list(kernel), list(pad), stride, act, planar_out, bias is not None, engine, flops)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        nd, N, Cin, Cout, S, O, kernel, pad, stride, act, planar_out, has_bias, engine, flops = ctx.meta
+        dy = _f32(dy)
+        if act != ACT_NONE:
+            dy = dy.contiguous()
+            g = torch.empty_like(y)
+            _lib.call("dfmir_act_bwd", y, dy, g, _lib.i64(y.numel()), act)
+            dy = g
+        elif engine == "umma":
+            dy = dy.contiguous()
+        dx = dw = db = None
+        ys = _cl_strides(dy, nd, planar_out)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
+            d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
+            wt = w.transpose(1, 2).contiguous()
+            if engine == "umma":
+                from . import umma
+                _run(lambda: umma.conv_dgrad(dy, wt, dx, d), flops, True)
+            else:
+                _run(lambda: _lib.call("dfmir_conv_dgrad", dy, wt, dx, ctypes.byref(d)), flops)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw = torch.zeros_like(w)
+            db = torch.zeros(Cout, dtype=w.dtype, device=w.device) if has_bias else None
+            d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(x, nd), ys)
+            if engine == "umma":
+                from . import umma
+                _run(lambda: umma.conv_wgrad(x, dy, dw, db, d), flops, True)
+            else:
+                _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops)
+        return dx, dw, db, None, None, None, None, None
+
+
+def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False):
+    """Convolution on a channels-last activation with a PyTorch-layout weight (Cout, Cin, *k).
+    Returns (N,*O,Cout), or the planar (N,Cout,*O) when planar_out."""
+    nd = weight.dim() - 2
+    kernel = list(weight.shape[2:])
+    pads = [pad] * nd if isinstance(pad, int) else list(pad)
+    Cout, Cin = weight.shape[:2]
+    # (Cout,Cin,*k) -> (taps, Cin, Cout); tiny tensors, torch autograd carries the permutation back
+    w = weight.reshape(Cout, Cin, -1).permute(2, 1, 0).contiguous()
+    return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out)
+
+
+class _InstNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, relu, out_pad, res_pad, eps):
+        _lib.require_cuda(x)
+        x = _f32(x).contiguous()
+        N, H, W, C = x.shape
+        if res is not None:
+            res = _f32(res).contiguous()
+            if tuple(res.shape) != (N, H + 2 * res_pad, W + 2 * res_pad, C):
+                raise _lib.DfmirError(f"instnorm: residual {tuple(res.shape)} does not match {tuple(x.shape)} pad {res_pad}")
+        y = torch.empty((N, H + 2 * out_pad, W + 2 * out_pad, C), dtype=x.dtype, device=x.device)
+        stats = torch.empty((N, C, 2), dtype=x.dtype, device=x.device)
+        nbytes = _lib.lib().dfmir_instnorm_workspace_bytes(N, C)
+        ws = workspace(nbytes, x.device)
+        _lib.call("dfmir_instnorm_fwd", x, res, y, stats, ws, _lib.size_t(ws.numel()), N, H, W, C, float(eps),
+                  int(relu), out_pad, res_pad)
+        ctx.save_for_backward(x, stats)
+        ctx.meta = (N, H, W, C, int(relu), out_pad, res_pad, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats = ctx.saved_tensors
+        N, H, W, C, relu, out_pad, res_pad, has_res = ctx.meta
+        dy = _f32(dy).contiguous()
+        dx = torch.empty_like(x)
+        dres = None
+        if has_res and ctx.needs_input_grad[1]:
+            dres = torch.empty((N, H + 2 * res_pad, W + 2 * res_pad, C), dtype=x.dtype, device=x.device)
+        ws = workspace(_lib.lib().dfmir_instnorm_workspace_bytes(N, C), x.device)
+        _lib.call("dfmir_instnorm_bwd", dy, x, stats, dx, dres, ws, _lib.size_t(ws.numel()), N, H, W, C, relu,
+                  out_pad, res_pad)
+        return dx, dres, None, None, None, None
+
+
+def instnorm_cl(x, relu=False, out_pad=0, res=None, res_pad=0, eps=1e-5):
+    """InstanceNorm2d(affine=False) [+ReLU] [+res] written with a reflected halo of width out_pad."""
+    return _InstNormFn.apply(x, res, relu, out_pad, res_pad, eps)
+
+
+class _PadReflectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        _lib.require_cuda(x)
+        x = _f32(x).contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty((N, H + 2 * pad, W + 2 * pad, C), dtype=x.dtype, device=x.device)
+        _lib.call("dfmir_pad_reflect_fwd", x, y, N, H, W, C, pad)
+        ctx.meta = (N, H, W, C, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C, pad = ctx.meta
+        dy = _f32(dy).contiguous()
+        dx = torch.empty((N, H, W, C), dtype=dy.dtype, device=dy.device)
+        _lib.call("dfmir_pad_reflect_bwd", dy, dx, N, H, W, C, pad)
+        return dx, None
+
+
+def pad_reflect_cl(x, pad):
+    return _PadReflectFn.apply(x, pad)
+
+
+class _BlurFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, up):
+        _lib.require_cuda(x)
+        x = _f32(x).contiguous()
+        N, H, W, C = x.shape
+        if up:
+            y = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+            _lib.call("dfmir_blur_up_fwd", x, y, N, H, W, C)
+        else:
+            y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+            _lib.call("dfmir_blur_down_fwd", x, y, N, H, W, C)
+        ctx.meta = (N, H, W, C, up)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, C, up = ctx.meta
+        dy = _f32(dy).contiguous()
+        dx = torch.empty((N, H, W, C), dtype=dy.dtype, device=dy.device)
+        _lib.call("dfmir_blur_up_bwd" if up else "dfmir_blur_down_bwd", dy, dx, N, H, W, C)
+        return dx, None
+
+
+def blur_down_cl(x):
+    return _BlurFn.apply(x, False)
+
+
+def blur_up_cl(x):
+    return _BlurFn.apply(x, True)
+
+
+class _UpCatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _lib.require_cuda(a, b)
+        a, b = _f32(a).contiguous(), _f32(b).contiguous()
+        nd = b.dim() - 2
+        N, shape, C1, C2 = b.shape[0], list(b.shape[1:1 + nd]), a.shape[-1], b.shape[-1]
+        if [2 * s for s in a.shape[1:1 + nd]] != shape:
+            raise _lib.DfmirError(f"upsample_concat: {tuple(a.shape)} x2 does not match skip {tuple(b.shape)}")
+        y = torch.empty((N, *shape, C1 + C2), dtype=a.dtype, device=a.device)
+        _lib.call("dfmir_upsample_concat_fwd", a, b, y, N, nd, shape, C1, C2)
+        ctx.meta = (N, nd, shape, C1, C2, tuple(a.shape), tuple(b.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, nd, shape, C1, C2, sa, sb = ctx.meta
+        dy = _f32(dy).contiguous()
+        da = torch.empty(sa, dtype=dy.dtype, device=dy.device) if ctx.needs_input_grad[0] else None
+        db = torch.empty(sb, dtype=dy.dtype, device=dy.device) if ctx.needs_input_grad[1] else None
+        if da is not None or db is not None:
+            _lib.call("dfmir_upsample_concat_bwd", dy, da, db, N, nd, shape, C1, C2)
+        return da, db
+
+
+def upsample_concat_cl(a, b):
+    """cat([nearest_x2(a), b], channel) for channels-last tensors (U-Net skip connection)."""
+    return _UpCatFn.apply(a, b)
+
+
+def _strides3(rows, cols, trans=False):
+    return (ctypes.c_longlong * 3)(0, 1, cols) if trans else (ctypes.c_longlong * 3)(0, cols, 1)
+
+
+def gemm(A, B, C, M, N, K, sA, sB, sC, bias=None, batch=1, alpha=1.0, accumulate=False, relu=False):
+    arr = lambda s: (ctypes.c_longlong * 3)(*[int(v) for v in s])
+    _lib.call("dfmir_gemm", A, B, bias, C, batch, M, N, K, arr(sA), arr(sB), arr(sC), float(alpha), int(accumulate), int(relu))
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = relu?(x W^T + b), x (M,K), W (N,K)  — nn.Linear of PatchSampleF.create_mlp."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        _lib.require_cuda(x, W)
+        x, W = _f32(x).contiguous(), _f32(W).contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+        gemm(x, W, y, M, N, K, (0, K, 1), (0, 1, K), (0, N, 1), bias=b, relu=relu)
+        ctx.save_for_backward(x, W, y if relu else None)
+        ctx.meta = (M, N, K, relu, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        M, N, K, relu, has_b = ctx.meta
+        dy = _f32(dy).contiguous()
+        if relu:
+            g = torch.empty_like(dy)
+            _lib.call("dfmir_act_bwd", y, dy, g, _lib.i64(y.numel()), ACT_RELU)
+            dy = g
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm(dy, W, dx, M, K, N, (0, N, 1), (0, K, 1), (0, K, 1))
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)   # dW (N,K) = dy^T x
+            gemm(dy, x, dW, N, K, M, (0, 1, N), (0, K, 1), (0, K, 1))
+        if has_b and ctx.needs_input_grad[2]:
+            ones = torch.ones(M, dtype=dy.dtype, device=dy.device)
+            db = torch.empty(N, dtype=dy.dtype, device=dy.device)
+            gemm(ones, dy, db, 1, N, M, (0, M, 1), (0, N, 1), (0, N, 1))
+        return dx, dW, db, None
+
+
+def linear(x, W, b, relu=False):
+    return _LinearFn.apply(x, W, b, relu)
+
+
+class _L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _lib.require_cuda(x)
+        x = _f32(x).contiguous()
+        rows, D = x.shape
+        y = torch.empty_like(x)
+        norms = torch.empty(rows, dtype=x.dtype, device=x.device)
+        _lib.call("dfmir_l2norm_fwd", x, y, norms, rows, D)
+        ctx.save_for_backward(x, norms)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, norms = ctx.saved_tensors
+        dy = _f32(dy).contiguous()
+        dx = torch.empty_like(x)
+        _lib.call("dfmir_l2norm_bwd", x, norms, dy, dx, x.shape[0], x.shape[1])
+        return dx
+
+
+def l2norm_rows(x):
+    """x / (||x||_2 + 1e-7) per row (reference Normalize, models/networks.py:493-502)."""
+    return _L2NormFn.apply(x)
+
+
+class _GatherFn(torch.autograd.Function):
+    """feat: logical (B,C,H,W) tensor of any strides; ids (P,) int64 -> (B*P, C)."""
+
+    @staticmethod
+    def forward(ctx, feat, ids):
+        _lib.require_cuda(feat, ids)
+        feat = _f32(feat)
+        B, C, H, W = feat.shape
+        P = ids.numel()
+        ids = ids.to(torch.int64).contiguous()
+        out = torch.empty((B * P, C), dtype=feat.dtype, device=feat.device)
+        st = feat.stride()
+        strides = (ctypes.c_longlong * 4)(st[0], st[2], st[3], st[1])
+        _lib.call("dfmir_gather_patches_fwd", feat, ids, out, B, P, C, W, strides)
+        ctx.save_for_backward(ids)
+        ctx.meta = (B, C, H, W, P)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        B, C, H, W, P = ctx.meta
+        dout = _f32(dout).contiguous()
+        dfeat = torch.zeros((B, H, W, C), dtype=dout.dtype, device=dout.device)
+        strides = (ctypes.c_longlong * 4)(H * W * C, W * C, C, 1)
+        _lib.call("dfmir_gather_patches_bwd", dout, ids, dfeat, B, P, C, W, strides)
+        return dfeat.permute(0, 3, 1, 2), None
+
+
+def gather_patches(feat, ids):
+    return _GatherFn.apply(feat, ids)
+
+
+class _PatchNCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, B, T):
+        _lib.require_cuda(q, k)
+        q, k = _f32(q).contiguous(), _f32(k).contiguous()
+        rows, D = q.shape
+        if rows % B or k.shape != q.shape:
+            raise _lib.DfmirError(f"PatchNCE: features {tuple(q.shape)} / {tuple(k.shape)} do not split into {B} images")
+        P = rows // B
+        S = torch.empty((B, P, P), dtype=q.dtype, device=q.device)
+        loss = torch.empty(rows, dtype=q.dtype, device=q.device)
+        _lib.call("dfmir_patchnce_fwd", q, k, S, loss, B, P, D, float(T))
+        ctx.save_for_backward(S, k)
+        ctx.meta = (B, P, D)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        S, k = ctx.saved_tensors
+        B, P, D = ctx.meta
+        g = _f32(g).contiguous()
+        work = torch.empty_like(S)
+        dq = torch.empty((B * P, D), dtype=g.dtype, device=g.device)
+        _lib.call("dfmir_patchnce_bwd", S, k, g, work, dq, B, P, D)
+        return dq, None, None, None
+
+
+def patchnce(q, k, batch, T):
+    return _PatchNCEFn.apply(q, k, batch, T)

@@ -184,10 +184,12 @@ class _L1MaskedFn(torch.autograd.Function):
         _lib.call("dfmir_l1_masked_fwd", a, b, mask, mu, mv, float(thr), out, ws, _lib.size_t(ws.numel()), _lib.i64(a.numel()))
         ctx.save_for_backward(a, b, mask, mu, mv, out)
         ctx.thr = float(thr)
-        return out[0]
+        msum = out[1]
+        ctx.mark_non_differentiable(msum)
+        return out[0], msum
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gm=None):
         a, b, mask, mu, mv, out = ctx.saved_tensors
         g = g.to(torch.float32).reshape(1).contiguous()
         da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
@@ -200,9 +202,11 @@ def calculate_L1_loss(src, tgt, mask=None):
     """sum(|src-tgt|*mask)/sum(mask) (reference: models/registration_model.py:255-263).
     Deviation: an empty mask yields a float 0 on the device instead of the reference's host-side
     `torch.tensor(0)`, which avoids the D2H sync of `torch.sum(mask) == 0`."""
-    return _L1MaskedFn.apply(src, tgt, mask, None, None, 0.0)
+    return _L1MaskedFn.apply(src, tgt, mask, None, None, 0.0)[0]
 
 
-def l1_threshold_masked(src, tgt, mu, mv, thr=-0.95):
-    """calculate_L1_loss with the mask (mu > thr) | (mv > thr) of registration_model.py:160-161 fused in."""
-    return _L1MaskedFn.apply(src, tgt, None, mu, mv, thr)
+def l1_threshold_masked(src, tgt, mu, mv, thr=-0.95, return_mask_sum=False):
+    """calculate_L1_loss with the mask (mu > thr) | (mv > thr) of registration_model.py:160-161 fused in.
+    return_mask_sum also returns sum(mask) as a device scalar (used for the global-batch normalisation)."""
+    loss, msum = _L1MaskedFn.apply(src, tgt, None, mu, mv, thr)
+    return (loss, msum) if return_mask_sum else loss

@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's training-step orchestrator
+(models/registration_model.py:34-263 REGISTRATIONModel; models/base_model.py BaseModel lifecycle
+:70-256) — the hot path named by BASELINE.json.  Same attributes (`netG`, `netF`, `netR`,
+`loss_*`, visuals), same method names and step order, so the reference's train.py loop drives it
+unchanged; every tensor op of the step runs in libdfmir_b200.so.
+
+Differences from the reference, all at the host level:
+  * `feat_k` encoder passes run under no_grad (the reference builds and discards their graph:
+    patchnce.py:17 detaches k);
+  * the two masked-L1 terms fuse the mask construction (registration_model.py:160-161) into the
+    loss kernel and return a device scalar 0 for an empty mask instead of forcing a host sync
+    (`torch.sum(mask) == 0`, :259);
+  * `./deform256.jpg` (:148) is decoded once and cached instead of every step; if the file is
+    absent a procedural 256x256 grid is used for the `dvf` visual;
+  * parallelize() (base_model.py:103-107) keeps one process per GPU: replicated weights, gradients
+    in one flat buffer all-reduced once per step over NCCL (no nn.DataParallel).
+"""
+import argparse
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib, layers, losses, networks, vxm
+from .patchnce import PatchNCELoss
+
+
+def default_options(**overrides):
+    """The reference's option defaults for this model (options/base_options.py:26-70,
+    options/train_options.py:23-40, registration_model.py:39-67 with CUT_mode=CUT)."""
+    opt = argparse.Namespace(
+        name='experiment_name', gpu_ids=[0], checkpoints_dir='./checkpoints', isTrain=True,
+        input_nc=1, output_nc=1, ngf=64, netG='resnet_9blocks', normG='instance', init_type='xavier',
+        init_gain=0.02, no_dropout=True, no_antialias=False, no_antialias_up=False,
+        batch_size=1, load_size=256, crop_size=256, preprocess='resize_and_crop', direction='AtoB',
+        lr=2e-4, beta1=0.5, beta2=0.999, n_epochs=150, n_epochs_decay=150, lr_policy='linear', epoch_count=1,
+        lr_decay_iters=50, continue_train=False, epoch='latest', verbose=False, pretrained_name=None,
+        CUT_mode='CUT', lambda_GAN=0.0, lambda_NCE=0.25, nce_idt=True, nce_layers='0,4,8,12,16',
+        nce_includes_all_negatives_from_minibatch=False, netF='mlp_sample', netF_nc=256, nce_T=0.07,
+        num_patches=256, flip_equivariance=False, gan_mode='lsgan', pool_size=0)
+    for k, v in overrides.items():
+        setattr(opt, k, v)
+    return opt
+
+
+_test_image_cache = {}
+
+
+def open_image_to_torch(path, size):
+    """CenterCrop(size) + ToTensor + Normalize(0.5, 0.5) of an image file (reference :14-23), cached."""
+    key = (os.path.abspath(path), size)
+    if key not in _test_image_cache:
+        if os.path.exists(path):
+            from PIL import Image
+            img = Image.open(path)
+            w, h = img.size
+            left, top = int(round((w - size) / 2.0)), int(round((h - size) / 2.0))
+            img = img.crop((left, top, left + size, top + size))
+            a = np.asarray(img, dtype=np.float32) / 255.0
+            if a.ndim == 2:
+                a = a[:, :, None]
+            t = torch.from_numpy(a).permute(2, 0, 1)
+        else:  # procedural deformation grid: lines every 16 pixels, 3 channels
+            g = np.ones((size, size), np.float32)
+            g[::16, :] = 0.0
+            g[:, ::16] = 0.0
+            t = torch.from_numpy(np.stack([g, g, g]))
+        _test_image_cache[key] = ((t - 0.5) / 0.5).unsqueeze(0).contiguous()
+    return _test_image_cache[key]
+
+
+def smooothing_loss(y_pred):
+    return losses.smooothing_loss(y_pred)
+
+
+class BaseModel:
+    """The slice of models/base_model.py the training loop touches."""
+
+    def __init__(self, opt):
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        self.device = torch.device('cuda:{}'.format(self.gpu_ids[0])) if self.gpu_ids else torch.device('cpu')
+        self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
+        self.loss_names, self.model_names, self.visual_names, self.optimizers, self.image_paths = [], [], [], [], []
+        self.metric = 0
+        self._flat_grad = None
+        self._world = 1
+
+    def setup(self, opt):
+        if self.isTrain:
+            self.schedulers = [networks.get_scheduler(optimizer, opt) for optimizer in self.optimizers]
+        if not self.isTrain or opt.continue_train:
+            self.load_networks(opt.epoch)
+        self.print_networks(opt.verbose)
+
+    def parallelize(self):
+        """One process per GPU (torchrun): replicate weights from rank 0 once, then average gradients
+        with a single NCCL all-reduce per step over a flat buffer that every `.grad` is a view of."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        self._world = dist.get_world_size()
+        params = []
+        for name in self.model_names:
+            net = getattr(self, 'net' + name)
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t.data, src=0)
+            params += [p for p in net.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in params)
+        self._flat_grad = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        # identical patch ids on every rank (networks.py:609 draws one permutation per layer)
+        seed = torch.randint(0, 2 ** 31 - 1, (1,), device=params[0].device)
+        dist.broadcast(seed, src=0)
+        torch.manual_seed(int(seed.item()))
+
+    def _zero_grads(self):
+        if self._flat_grad is not None:
+            self._flat_grad.zero_()
+        else:
+            for opt_ in self.optimizers:
+                opt_.zero_grad()
+
+    def _sync_grads(self):
+        if self._flat_grad is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._flat_grad)
+            self._flat_grad.mul_(1.0 / self._world)
+
+    def data_dependent_initialize(self, data):
+        pass
+
+    def eval(self):
+        for name in self.model_names:
+            getattr(self, 'net' + name).eval()
+
+    def test(self):
+        with torch.no_grad():
+            self.forward()
+            self.compute_visuals()
+
+    def compute_visuals(self):
+        pass
+
+    def get_image_paths(self):
+        return self.image_paths
+
+    def update_learning_rate(self):
+        for scheduler in self.schedulers:
+            if self.opt.lr_policy == 'plateau':
+                scheduler.step(self.metric)
+            else:
+                scheduler.step()
+        print('learning rate = %.7f' % self.optimizers[0].param_groups[0]['lr'])
+
+    def get_current_visuals(self):
+        return OrderedDict((name, getattr(self, name)) for name in self.visual_names)
+
+    def get_current_losses(self):
+        return OrderedDict((name, float(getattr(self, 'loss_' + name))) for name in self.loss_names)
+
+    def save_networks(self, epoch):
+        os.makedirs(self.save_dir, exist_ok=True)
+        for name in self.model_names:
+            net = getattr(self, 'net' + name)
+            sd = OrderedDict((k, v.detach().cpu()) for k, v in net.state_dict().items())
+            torch.save(sd, os.path.join(self.save_dir, '%s_net_%s.pth' % (epoch, name)))
+
+    def load_networks(self, epoch):
+        for name in self.model_names:
+            load_dir = os.path.join(self.opt.checkpoints_dir, self.opt.pretrained_name) \
+                if self.opt.isTrain and self.opt.pretrained_name is not None else self.save_dir
+            load_path = os.path.join(load_dir, '%s_net_%s.pth' % (epoch, name))
+            print('loading the model from %s' % load_path)
+            state_dict = torch.load(load_path, map_location=str(self.device))
+            if hasattr(state_dict, '_metadata'):
+                del state_dict._metadata
+            getattr(self, 'net' + name).load_state_dict(state_dict)
+
+    def print_networks(self, verbose):
+        print('---------- Networks initialized -------------')
+        for name in self.model_names:
+            net = getattr(self, 'net' + name)
+            num_params = sum(p.numel() for p in net.parameters())
+            if verbose:
+                print(net)
+            print('[Network %s] Total number of parameters : %.3f M' % (name, num_params / 1e6))
+        print('-----------------------------------------------')
+
+
+class REGISTRATIONModel(BaseModel):
+    def __init__(self, opt):
+        BaseModel.__init__(self, opt)
+        self.loss_names = ['G', 'NCE', 'R', 'smooth', 'local']
+        self.visual_names = ['real_A', 'fake_B', 'real_B', 'dvf', 'registered', 'regA']
+        self.nce_layers = [int(i) for i in self.opt.nce_layers.split(',')]
+        if opt.nce_idt and self.isTrain:
+            self.loss_names += ['NCE_Y']
+            self.visual_names += ['idt_B']
+        self.model_names = ['G', 'F', 'R'] if self.isTrain else ['G', 'R']
+        if opt.lambda_GAN > 0.0:
+            raise NotImplementedError("dfmir_b200: the discriminator-free model (lambda_GAN = 0, the reference default)")
+        self.netG = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.netG, opt.normG, not opt.no_dropout,
+                                      opt.init_type, opt.init_gain, opt.no_antialias, opt.no_antialias_up,
+                                      self.gpu_ids, opt)
+        self.netF = networks.define_F(opt.input_nc, opt.netF, opt.normG, not opt.no_dropout, opt.init_type,
+                                      opt.init_gain, opt.no_antialias, self.gpu_ids, opt)
+        nb_features = [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]]
+        vol_shape = (opt.crop_size, opt.crop_size)
+        self.netR = vxm.VxmDense(vol_shape, nb_features, int_steps=7, bidir=True).to(self.device)
+        self.netR.train()
+        self.spatialTransformer = layers.SpatialTransformer(vol_shape).to(self.device)
+        if self.isTrain:
+            self.criterionNCE = [PatchNCELoss(opt).to(self.device) for _ in self.nce_layers]
+            self.criterionNCC = losses.NCC_Loss(self.device, name='ncc', kernel_var=[9, 9], kernel_type='mean')
+            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2))
+            self.optimizer_R = torch.optim.Adam(self.netR.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2))
+            self.optimizers.append(self.optimizer_G)
+            self.optimizers.append(self.optimizer_R)
+
+    def data_dependent_initialize(self, data):
+        self.set_input(data)
+        bs_per_gpu = self.real_A.size(0) // max(len(self.opt.gpu_ids), 1)
+        self.real_A = self.real_A[:bs_per_gpu]
+        self.real_B = self.real_B[:bs_per_gpu]
+        self.forward()
+        if self.opt.isTrain:
+            self.compute_G_loss().backward()
+            if self.opt.lambda_NCE > 0.0:
+                self.optimizer_F = torch.optim.Adam(self.netF.parameters(), lr=self.opt.lr,
+                                                    betas=(self.opt.beta1, self.opt.beta2))
+                self.optimizers.append(self.optimizer_F)
+
+    def optimize_parameters(self):
+        self.forward()
+        y_output = self.netR(self.real_A, self.real_B)
+        pos_flow = y_output[2]
+        self.registered = self.spatialTransformer(self.fake_B, pos_flow)
+        self.regA = y_output[0]
+        test_image = open_image_to_torch("./deform256.jpg", self.opt.crop_size).to(self.device, non_blocking=True)
+        with torch.no_grad():
+            self.dvf = self.spatialTransformer(test_image.expand(pos_flow.shape[0], -1, -1, -1).contiguous()
+                                               if pos_flow.shape[0] > 1 else test_image, pos_flow)
+        self._zero_grads()
+
+        self.loss_G = self.compute_G_loss()
+        # masked L1 terms: mask = (u > -0.95) | (v > -0.95) built inside the loss kernel (:160-161)
+        self.loss_local = self.calculate_NCE_loss(self.real_B, self.regA) * 0.25
+        l1_a = self._masked_l1(self.registered, self.real_B, self.real_B, self.registered)
+        l1_b = self._masked_l1(self.idt_B, self.registered, self.idt_B, self.registered)
+        self.loss_R = l1_a * 1.0 + l1_b * 1.0 + self.loss_local * 1.0
+        self.loss_smooth = smooothing_loss(pos_flow) * 0.20
+        all_G_loss = self.loss_R + self.loss_G + self.loss_smooth
+        all_G_loss.backward()
+        self._sync_grads()
+        self.optimizer_G.step()
+        self.optimizer_R.step()
+        if self.opt.netF == 'mlp_sample':
+            self.optimizer_F.step()
+
+    def _masked_l1(self, src, tgt, mu, mv):
+        loss, msum = losses.l1_threshold_masked(src, tgt, mu, mv, thr=-0.95, return_mask_sum=True)
+        if self._world > 1:
+            # exact global-batch normalisation: sum over ranks of |d|*m / sum over ranks of m
+            import torch.distributed as dist
+            total = msum.detach().clone()
+            dist.all_reduce(total)
+            scale = torch.where(total > 0, msum.detach() * self._world / total.clamp_min(1e-20), torch.ones_like(total))
+            loss = loss * scale
+        return loss
+
+    def set_input(self, input):
+        AtoB = self.opt.direction == 'AtoB'
+        self.real_A = input['A' if AtoB else 'B'].to(self.device, non_blocking=True)
+        self.real_B = input['B' if AtoB else 'A'].to(self.device, non_blocking=True)
+        self.image_paths = input.get('A_paths' if AtoB else 'B_paths', [])
+
+    def forward(self):
+        self.real = torch.cat((self.real_A, self.real_B), dim=0)
+        if self.opt.flip_equivariance:
+            self.flipped_for_equivariance = self.opt.isTrain and (np.random.random() < 0.5)
+            if self.flipped_for_equivariance:
+                self.real = torch.flip(self.real, [3])
+        self.fake = self.netG(self.real)
+        self.fake_B = self.fake[:self.real_A.size(0)]
+        self.idt_B = self.fake[self.real_A.size(0):]
+
+    def compute_G_loss(self):
+        if self.opt.lambda_NCE > 0.0:
+            self.loss_NCE = self.calculate_NCE_loss(self.real_A, self.fake_B)
+        else:
+            self.loss_NCE, self.loss_NCE_bd = 0.0, 0.0
+        if self.opt.nce_idt and self.opt.lambda_NCE > 0.0:
+            self.loss_NCE_Y = self.calculate_NCE_loss(self.real_B, self.idt_B)
+            loss_NCE_both = (self.loss_NCE + self.loss_NCE_Y) * 0.5
+        else:
+            loss_NCE_both = self.loss_NCE
+        self.loss_G_GAN = 0.0
+        self.loss_G = self.loss_G_GAN + loss_NCE_both
+        return self.loss_G
+
+    def calculate_NCE_loss(self, src, tgt, patch_ids=None):
+        n_layers = len(self.nce_layers)
+        feat_q = self.netG(tgt, self.nce_layers, encode_only=True)
+        if self.opt.flip_equivariance and self.flipped_for_equivariance:
+            feat_q = [torch.flip(fq, [3]) for fq in feat_q]
+        mlp_ready = (not self.netF.use_mlp) or self.netF.mlp_init
+        with torch.no_grad():   # k is detached inside PatchNCELoss (patchnce.py:17)
+            feat_k = self.netG(src, self.nce_layers, encode_only=True)
+            if not mlp_ready:
+                self.netF.create_mlp(feat_k)
+            feat_k_pool, sample_ids = self.netF(feat_k, self.opt.num_patches, patch_ids)
+        feat_q_pool, _ = self.netF(feat_q, self.opt.num_patches, sample_ids)
+        total_nce_loss = 0.0
+        for f_q, f_k, crit, nce_layer in zip(feat_q_pool, feat_k_pool, self.criterionNCE, self.nce_layers):
+            loss = crit(f_q, f_k) * self.opt.lambda_NCE
+            total_nce_loss += loss.mean()
+        return total_nce_loss / n_layers
+
+    def calculate_L1_loss(self, src, tgt, mask):
+        return losses.calculate_L1_loss(src, tgt, mask)
+
+
+RegistrationModel = REGISTRATIONModel

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DFMIR_ABI_VERSION 1
+#define DFMIR_ABI_VERSION 2
 
 #define DFMIR_INTERP_LINEAR 0
 #define DFMIR_INTERP_NEAREST 1
@@ -95,6 +95,82 @@ int dfmir_l1_masked_fwd(const float* a, const float* b, const uint8_t* mask, con
 int dfmir_l1_masked_bwd(const float* a, const float* b, const uint8_t* mask, const float* mu, const float* mv,
                         float thr, const float* fwd_out, const float* grad_loss, float* da, float* db,
                         long long n, void* stream);
+
+/* ---- K1/K2: nn.Conv2d / nn.Conv3d — models/networks.py:983,995,1016,1023,1201,1214 (ResnetGenerator),
+ * models/voxelmorph/torchvoxelmorph/networks.py:1515 (ConvBlock) and :1077 (flow head).
+ * Activations are channels-last with explicit element strides {n, spatial..., c} (so padded buffers,
+ * interior views and the planar flow output need no copy); zero padding only (reflection padding is
+ * materialised by the producer, see dfmir_instnorm_fwd / dfmir_pad_reflect_fwd).
+ * Weights: forward / wgrad layout [tap][Cin][Cout], tap = (kd*KH + kh)*KW + kw; dgrad layout
+ * [tap][Cout][Cin].  The descriptor always describes the FORWARD convolution. */
+#define DFMIR_ACT_NONE 0
+#define DFMIR_ACT_LEAKY 1 /* LeakyReLU(0.2), vxm networks.py:1516 */
+#define DFMIR_ACT_TANH 2  /* models/networks.py:1024 */
+#define DFMIR_ACT_RELU 3
+typedef struct dfmir_conv_desc {
+  int nd;                 /* 2 or 3 */
+  int N, Cin, Cout;
+  int in_shape[3], out_shape[3], kernel[3], pad[3];
+  int stride;             /* same on every axis (1 or 2 in the reference) */
+  int act;                /* epilogue activation of the forward (DFMIR_ACT_*) */
+  long long x_strides[5]; /* input  element strides {n, spatial[nd], c} */
+  long long y_strides[5]; /* output element strides {n, spatial[nd], c} */
+} dfmir_conv_desc;
+/* engine: 0 = fp32 CUDA cores (exact fp32 accumulate, any shape); 1 = tcgen05 tensor cores (TF32
+ * operands, fp32 accumulate) — only for shapes dfmir_conv_umma_supported() accepts. */
+int dfmir_conv_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
+                   void* stream);
+int dfmir_conv_dgrad(const float* dy, const float* wt, float* dx, const dfmir_conv_desc* d, void* stream);
+/* dw [tap][Cin][Cout] and db [Cout] (nullable) are accumulated into: zero-fill them first. */
+int dfmir_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d,
+                     void* stream);
+/* dx = dy * act'(y) for the epilogue activations, contiguous arrays of n elements */
+int dfmir_act_bwd(const float* y, const float* dy, float* dx, long long n, int act, void* stream);
+
+/* ---- InstanceNorm2d(affine=False) [+ReLU] [+skip add] [+ReflectionPad2d] — models/networks.py:984,
+ * 996,1020 and ResnetBlock :1193-1221.  x (N,H,W,C) channels-last; y (N,H+2p,W+2p,C) with a mirrored
+ * halo of width p = out_pad; res (nullable) (N,H+2rp,W+2rp,C) is read at its interior.
+ * stats (N,C,2) = {mean, rstd}; ws: dfmir_instnorm_workspace_bytes. */
+size_t dfmir_instnorm_workspace_bytes(int N, int C);
+int dfmir_instnorm_fwd(const float* x, const float* res, float* y, float* stats, void* ws, size_t ws_bytes, int N,
+                       int H, int W, int C, float eps, int relu, int out_pad, int res_pad, void* stream);
+/* dy (N,H+2p,W+2p,C) -> dx (N,H,W,C); dres (nullable, (N,H+2rp,W+2rp,C), halo zeroed here) */
+int dfmir_instnorm_bwd(const float* dy, const float* x, const float* stats, float* dx, float* dres, void* ws,
+                       size_t ws_bytes, int N, int H, int W, int C, int relu, int out_pad, int res_pad,
+                       void* stream);
+/* ---- nn.ReflectionPad2d — models/networks.py:982,1022 */
+int dfmir_pad_reflect_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, void* stream);
+int dfmir_pad_reflect_bwd(const float* dy, float* dx, int N, int H, int W, int C, int pad, void* stream);
+/* ---- Downsample / Upsample (anti-aliased) — models/networks.py:37-60, 73-93; channels-last */
+int dfmir_blur_down_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int dfmir_blur_down_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+int dfmir_blur_up_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int dfmir_blur_up_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+/* ---- nn.Upsample(x2, nearest) + torch.cat([x, skip], 1) — vxm networks.py:99-102; channels-last.
+ * a (N,*shape/2,C1), b (N,*shape,C2) -> y (N,*shape,C1+C2) */
+int dfmir_upsample_concat_fwd(const float* a, const float* b, float* y, int N, int nd, const int* shape, int C1,
+                              int C2, void* stream);
+int dfmir_upsample_concat_bwd(const float* dy, float* da, float* db, int N, int nd, const int* shape, int C1,
+                              int C2, void* stream);
+
+/* ---- K6: PatchNCELoss.forward — models/patchnce.py:14-55.  q,k (B*P, D); S (B,P,P) scratch that the
+ * forward leaves holding dLoss/dS; loss (B*P).  k is treated as detached (patchnce.py:17). */
+int dfmir_patchnce_fwd(const float* q, const float* k, float* S, float* loss, int B, int P, int D, float T,
+                       void* stream);
+int dfmir_patchnce_bwd(const float* S, const float* k, const float* g, float* work, float* dq, int B, int P, int D,
+                       void* stream);
+/* ---- PatchSampleF — models/networks.py:597-624: patch gather, MLP products, L2 normalisation */
+int dfmir_gather_patches_fwd(const float* feat, const long long* ids, float* out, int B, int P, int C, int Wd,
+                             const long long* strides, void* stream);
+int dfmir_gather_patches_bwd(const float* dout, const long long* ids, float* dfeat, int B, int P, int C, int Wd,
+                             const long long* strides, void* stream);
+int dfmir_l2norm_fwd(const float* x, float* y, float* norms, int rows, int D, void* stream);
+int dfmir_l2norm_bwd(const float* x, const float* norms, const float* dy, float* dx, int rows, int D, void* stream);
+/* strided batched product C[b](m,n) (+)= alpha * sum_k A[b](m,k) B[b](k,n) (+ bias[n]) (ReLU);
+ * strides {batch,row,col} in elements.  nn.Linear of PatchSampleF.create_mlp (networks.py:587-595). */
+int dfmir_gemm(const float* A, const float* B, const float* bias, float* C, int batch, int M, int N, int K,
+               const long long* sA, const long long* sB, const long long* sC, float alpha, int accumulate, int relu,
+               void* stream);
 
 #ifdef __cplusplus
 }

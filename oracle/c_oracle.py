@@ -102,3 +102,62 @@ def l1_masked(a, b, mask=None, mu=None, mv=None, thr=-0.95):
     out = np.zeros(2, dtype=np.float32)
     lib().orc_l1_masked(_p(a), _p(b), _p(m8), _p(mu), _p(mv), ctypes.c_float(thr), _p(out), ctypes.c_longlong(a.size))
     return out
+
+
+# ---------------------------------------------------------------- network layers (planar NCHW / NCDHW)
+def conv(x, w, b=None, stride=1, pad=0):
+    x, w = _f(x), _f(w)
+    nd = x.ndim - 2
+    N, Cin = x.shape[:2]
+    Cout = w.shape[0]
+    O = [(x.shape[2 + a] + 2 * pad - w.shape[2 + a]) // stride + 1 for a in range(nd)]
+    y = np.empty((N, Cout, *O), dtype=np.float32)
+    b = None if b is None else _f(b)
+    lib().orc_conv(_p(x), _p(w), _p(b), _p(y), N, Cin, Cout, nd, _ints(x.shape[2:]), _ints(w.shape[2:]), int(stride), int(pad))
+    return y
+
+
+def instnorm(x, eps=1e-5):
+    x = _f(x)
+    y = np.empty_like(x)
+    lib().orc_instnorm(_p(x), _p(y), x.shape[0] * x.shape[1], ctypes.c_longlong(int(np.prod(x.shape[2:]))), ctypes.c_float(eps))
+    return y
+
+
+def pad_reflect(x, p):
+    x = _f(x)
+    N, C, H, W = x.shape
+    y = np.empty((N, C, H + 2 * p, W + 2 * p), dtype=np.float32)
+    lib().orc_pad_reflect(_p(x), _p(y), N * C, H, W, int(p))
+    return y
+
+
+def blur_down(x):
+    x = _f(x)
+    N, C, H, W = x.shape
+    y = np.empty((N, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1), dtype=np.float32)
+    lib().orc_blur_down(_p(x), _p(y), N * C, H, W)
+    return y
+
+
+def blur_up(x):
+    x = _f(x)
+    N, C, H, W = x.shape
+    y = np.empty((N, C, 2 * H, 2 * W), dtype=np.float32)
+    lib().orc_blur_up(_p(x), _p(y), N * C, H, W)
+    return y
+
+
+def upsample_nn(x):
+    x = _f(x)
+    y = np.empty(x.shape[:2] + tuple(2 * s for s in x.shape[2:]), dtype=np.float32)
+    lib().orc_upsample_nn(_p(x), _p(y), x.shape[0] * x.shape[1], x.ndim - 2, _ints(x.shape[2:]))
+    return y
+
+
+def patchnce(q, k, batch, T=0.07):
+    q, k = _f(q), _f(k)
+    rows, D = q.shape
+    loss = np.empty(rows, dtype=np.float32)
+    lib().orc_patchnce(_p(q), _p(k), _p(loss), int(batch), rows // int(batch), D, ctypes.c_float(T))
+    return loss

@@ -255,3 +255,153 @@ void orc_l1_masked(const float* a, const float* b, const uint8_t* mask, const fl
   out[0] = m == 0.0 ? 0.f : (float)(s / m);
   out[1] = (float)m;
 }
+
+/* ===================================================================================
+ * Network layers (NCHW / NCDHW planar fp32, as the reference keeps them)
+ *   orc_conv          nn.Conv2d / nn.Conv3d (zero padding, stride)     models/networks.py:983..1214,
+ *                                                                       vxm networks.py:1515,1077
+ *   orc_instnorm      nn.InstanceNorm2d(affine=False), eps 1e-5        models/networks.py:125
+ *   orc_pad_reflect   nn.ReflectionPad2d                               models/networks.py:982,1022,1193
+ *   orc_blur_down     Downsample (reflect pad 1, [1,2,1]^2/16, s2)     models/networks.py:37-60
+ *   orc_blur_up       Upsample (replicate pad, conv_transpose 4x4, crop) models/networks.py:73-93
+ *   orc_upsample_nn   nn.Upsample(scale_factor=2, 'nearest')           vxm networks.py:62,100
+ *   orc_patchnce      PatchNCELoss.forward                             models/patchnce.py:14-55
+ * =================================================================================== */
+
+/* x (N,Cin,*I) w (Cout,Cin,*K) b (Cout, nullable) -> y (N,Cout,*O); nd 2 or 3 (2-D: leading dims 1) */
+void orc_conv(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int nd,
+              const int* I_, const int* K_, int stride, int pad) {
+  int I[3] = {1, 1, 1}, K[3] = {1, 1, 1}, O[3] = {1, 1, 1}, P[3] = {0, 0, 0};
+  for (int a = 0; a < nd; ++a) {
+    I[a + 3 - nd] = I_[a]; K[a + 3 - nd] = K_[a]; P[a + 3 - nd] = pad;
+    O[a + 3 - nd] = (I_[a] + 2 * pad - K_[a]) / stride + 1;
+  }
+  const long long ivox = (long long)I[0] * I[1] * I[2], ovox = (long long)O[0] * O[1] * O[2];
+  const long long kvox = (long long)K[0] * K[1] * K[2];
+  for (int n = 0; n < N; ++n)
+    for (int co = 0; co < Cout; ++co)
+      for (int oz = 0; oz < O[0]; ++oz)
+        for (int oy = 0; oy < O[1]; ++oy)
+          for (int ox = 0; ox < O[2]; ++ox) {
+            double acc = 0.0; /* wide accumulator: the reference's blocked fp32 sums are order-dependent */
+            for (int ci = 0; ci < Cin; ++ci)
+              for (int kz = 0; kz < K[0]; ++kz) {
+                const int iz = oz * stride - P[0] + kz;
+                if (iz < 0 || iz >= I[0]) continue;
+                for (int ky = 0; ky < K[1]; ++ky) {
+                  const int iy = oy * stride - P[1] + ky;
+                  if (iy < 0 || iy >= I[1]) continue;
+                  for (int kx = 0; kx < K[2]; ++kx) {
+                    const int ix = ox * stride - P[2] + kx;
+                    if (ix < 0 || ix >= I[2]) continue;
+                    acc += (double)x[((long long)n * Cin + ci) * ivox + ((long long)iz * I[1] + iy) * I[2] + ix] *
+                           (double)w[((long long)co * Cin + ci) * kvox + ((long long)kz * K[1] + ky) * K[2] + kx];
+                  }
+                }
+              }
+            if (b) acc += (double)b[co];
+            y[((long long)n * Cout + co) * ovox + ((long long)oz * O[1] + oy) * O[2] + ox] = (float)acc;
+          }
+}
+
+/* per (n,c) plane of HW elements: (x - mean) / sqrt(var_biased + eps) */
+void orc_instnorm(const float* x, float* y, int NC, long long HW, float eps) {
+  for (int p = 0; p < NC; ++p) {
+    const float* xp = x + (long long)p * HW;
+    double s = 0, ss = 0;
+    for (long long i = 0; i < HW; ++i) s += xp[i];
+    const double m = s / (double)HW;
+    for (long long i = 0; i < HW; ++i) ss += ((double)xp[i] - m) * ((double)xp[i] - m);
+    const double r = 1.0 / sqrt(ss / (double)HW + (double)eps);
+    for (long long i = 0; i < HW; ++i) y[(long long)p * HW + i] = (float)(((double)xp[i] - m) * r);
+  }
+}
+
+static int reflect_i(int i, int n) { if (i < 0) i = -i; if (i >= n) i = 2 * (n - 1) - i; return i; }
+static int clamp_i(int i, int n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
+
+void orc_pad_reflect(const float* x, float* y, int NC, int H, int W, int p) {
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  for (int c = 0; c < NC; ++c)
+    for (int h = 0; h < HP; ++h)
+      for (int w = 0; w < WP; ++w)
+        y[((long long)c * HP + h) * WP + w] = x[((long long)c * H + reflect_i(h - p, H)) * W + reflect_i(w - p, W)];
+}
+
+/* F.conv2d(reflect_pad(x,1), [1,2,1]x[1,2,1]/16, stride 2, groups=C) */
+void orc_blur_down(const float* x, float* y, int NC, int H, int W) {
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  static const float f[3] = {1.f, 2.f, 1.f};
+  for (int c = 0; c < NC; ++c)
+    for (int oh = 0; oh < OH; ++oh)
+      for (int ow = 0; ow < OW; ++ow) {
+        float acc = 0.f;
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b)
+            acc += x[((long long)c * H + reflect_i(2 * oh - 1 + a, H)) * W + reflect_i(2 * ow - 1 + b, W)] *
+                   (f[a] * f[b] / 16.f);
+        y[((long long)c * OH + oh) * OW + ow] = acc;
+      }
+}
+
+/* conv_transpose2d(replicate_pad(x,1), [1,3,3,1]x[1,3,3,1]/64*4, stride 2, padding 2)[1:,1:][:-1,:-1],
+ * restated literally: scatter every padded input sample through the 4x4 filter, then crop. */
+void orc_blur_up(const float* x, float* y, int NC, int H, int W) {
+  static const float f[4] = {1.f, 3.f, 3.f, 1.f};
+  const int PH = H + 2, PW = W + 2;
+  const int TH = (PH - 1) * 2 - 4 + 4, TW = (PW - 1) * 2 - 4 + 4; /* conv_transpose output */
+  const int OH = 2 * H, OW = 2 * W;
+  float* tmp = (float*)malloc(sizeof(float) * (size_t)TH * TW);
+  for (int c = 0; c < NC; ++c) {
+    memset(tmp, 0, sizeof(float) * (size_t)TH * TW);
+    for (int i = 0; i < PH; ++i)
+      for (int j = 0; j < PW; ++j) {
+        const float v = x[((long long)c * H + clamp_i(i - 1, H)) * W + clamp_i(j - 1, W)];
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) {
+            const int oi = 2 * i - 2 + a, oj = 2 * j - 2 + b;
+            if (oi < 0 || oi >= TH || oj < 0 || oj >= TW) continue;
+            tmp[(long long)oi * TW + oj] += v * (f[a] * f[b] / 64.f * 4.f);
+          }
+      }
+    for (int oh = 0; oh < OH; ++oh)
+      for (int ow = 0; ow < OW; ++ow) y[((long long)c * OH + oh) * OW + ow] = tmp[(long long)(oh + 1) * TW + ow + 1];
+  }
+  free(tmp);
+}
+
+/* nearest x2: x (NC,*S) -> y (NC,*2S), nd 2 or 3 */
+void orc_upsample_nn(const float* x, float* y, int NC, int nd, const int* S_) {
+  int S[3] = {1, 1, 1};
+  for (int a = 0; a < nd; ++a) S[a + 3 - nd] = S_[a];
+  const int O0 = nd == 3 ? 2 * S[0] : 1, O1 = 2 * S[1], O2 = 2 * S[2];
+  for (int c = 0; c < NC; ++c)
+    for (int z = 0; z < O0; ++z)
+      for (int yy = 0; yy < O1; ++yy)
+        for (int xx = 0; xx < O2; ++xx)
+          y[(((long long)c * O0 + z) * O1 + yy) * O2 + xx] =
+              x[(((long long)c * S[0] + (nd == 3 ? z / 2 : 0)) * S[1] + yy / 2) * S[2] + xx / 2];
+}
+
+/* q,k (B*P, D): loss[r] = logsumexp([q.k_pos, q.k_j (j != i; -10 at j == i)] / T) - q.k_pos / T */
+void orc_patchnce(const float* q, const float* k, float* loss, int B, int P, int D, float T) {
+  float* row = (float*)malloc(sizeof(float) * (size_t)(P + 1));
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < P; ++i) {
+      const float* qi = q + ((long long)b * P + i) * D;
+      for (int j = 0; j < P; ++j) {
+        const float* kj = k + ((long long)b * P + j) * D;
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) acc += qi[d] * kj[d];
+        row[j + 1] = acc;
+      }
+      row[0] = row[i + 1];
+      row[i + 1] = -10.0f;
+      float mx = -INFINITY;
+      for (int j = 0; j <= P; ++j) { row[j] = row[j] / T; if (row[j] > mx) mx = row[j]; }
+      double s = 0;
+      for (int j = 0; j <= P; ++j) s += exp((double)row[j] - mx);
+      loss[(long long)b * P + i] = (float)((double)mx + log(s) - (double)row[0]);
+    }
+  free(row);
+}

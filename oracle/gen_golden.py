@@ -179,7 +179,164 @@ def gen_ops():
     save("losses", **out)
 
 
-SECTIONS = {"ops": gen_ops}
+def det_randperm(counter):
+    """Deterministic stand-in for torch.randperm (PatchSampleF draws, models/networks.py:609): the k-th
+    call returns numpy RandomState(9000 + k).permutation(n).  Tests install the same function."""
+    def f(n, device=None, **kw):
+        counter[0] += 1
+        return torch.from_numpy(np.random.RandomState(9000 + counter[0]).permutation(int(n))).to(device or 'cpu')
+    return f
+
+
+def sd_np(sd, prefix):
+    return {f"{prefix}/{k}": v.detach().cpu().numpy().copy() for k, v in sd.items() if not k.endswith('.grid')}
+
+
+def gen_nets():
+    import_reference()
+    from models import networks as rn
+    from models.patchnce import PatchNCELoss
+    import models.voxelmorph.torchvoxelmorph as rvxm
+    import argparse
+    out = {}
+
+    # ---- layer-level: blur-pool down / up, instance norm (+relu), reflection pad: fwd + bwd
+    torch.manual_seed(7)
+    x = t(gi.weights(201, (2, 6, 12, 16), 1.0)).requires_grad_()
+    for name, mod in (("down", rn.Downsample(6)), ("up", rn.Upsample(6))):
+        y = mod(x)
+        gy = t(gi.weights(202, tuple(y.shape), 1.0))
+        y.backward(gy)
+        out[f"layer/{name}"] = y.detach().numpy(); out[f"layer/{name}_dx"] = x.grad.numpy().copy(); x.grad = None
+    blk = rn.ResnetBlock(6, 'reflect', rn.get_norm_layer('instance'), False, True)
+    rn.init_weights(blk, 'xavier', 0.5)
+    y = blk(x)
+    y.backward(t(gi.weights(203, tuple(y.shape), 1.0)))
+    out["layer/resblock"] = y.detach().numpy(); out["layer/resblock_dx"] = x.grad.numpy().copy()
+    out.update(sd_np(blk.state_dict(), "layer/resblock_sd"))
+    out.update({f"layer/resblock_grad/{k}": v.grad.numpy() for k, v in blk.named_parameters()})
+
+    # ---- ResnetGenerator (ngf 8, 3 blocks, 32x40 input): full forward, encode_only features, backward
+    torch.manual_seed(11)
+    G = rn.define_G(1, 1, 8, 'resnet_4blocks', 'instance', False, 'xavier', 0.5, False, False, [], None)
+    xin = t(gi.image_textured(211, 2, (32, 40))).requires_grad_()
+    fake, feats = G(xin, [0, 4, 8, 12, 14], encode_only=False)
+    out["G/in"] = xin.detach().numpy()
+    out["G/fake"] = fake.detach().numpy()
+    for i, f in enumerate(feats):
+        out[f"G/feat{i}"] = f.detach().numpy()
+    enc = G(xin, [0, 4, 8, 12, 14], encode_only=True)
+    assert all(torch.equal(a, b) for a, b in zip(enc, feats))
+    loss = (fake * t(gi.weights(212, tuple(fake.shape), 1.0))).sum() + sum(
+        (f * t(gi.weights(213 + i, tuple(f.shape), 0.1))).sum() for i, f in enumerate(feats))
+    loss.backward()
+    out["G/dx"] = xin.grad.numpy()
+    out.update(sd_np(G.state_dict(), "G/sd"))
+    out.update({f"G/grad/{k}": v.grad.numpy() for k, v in G.named_parameters()})
+
+    # ---- PatchSampleF + PatchNCELoss
+    torch.manual_seed(12)
+    opt = argparse.Namespace(netF_nc=32, batch_size=2, nce_T=0.07, nce_includes_all_negatives_from_minibatch=False)
+    netF = rn.define_F(1, 'mlp_sample', 'instance', False, 'xavier', 0.5, False, [], opt)
+    fq = [t(gi.weights(221, (2, 1, 20, 24), 1.0)).requires_grad_(), t(gi.weights(222, (2, 16, 10, 12), 1.0)).requires_grad_()]
+    fk = [t(gi.weights(223, (2, 1, 20, 24), 1.0)), t(gi.weights(224, (2, 16, 10, 12), 1.0))]
+    cnt = [0]
+    torch_randperm = torch.randperm
+    torch.randperm = det_randperm(cnt)
+    try:
+        k_pool, ids = netF(fk, 48, None)
+    finally:
+        torch.randperm = torch_randperm
+    q_pool, _ = netF(fq, 48, ids)
+    crit = PatchNCELoss(opt)
+    total = 0
+    for i, (q, k) in enumerate(zip(q_pool, k_pool)):
+        l = crit(q, k)
+        out[f"F/loss{i}"] = l.detach().numpy(); out[f"F/q{i}"] = q.detach().numpy(); out[f"F/k{i}"] = k.detach().numpy()
+        out[f"F/ids{i}"] = ids[i].numpy()
+        total = total + l.mean()
+    total.backward()
+    out["F/dq0"] = fq[0].grad.numpy(); out["F/dq1"] = fq[1].grad.numpy()
+    out.update(sd_np(netF.state_dict(), "F/sd"))
+    out.update({f"F/grad/{k}": v.grad.numpy() for k, v in netF.named_parameters()})
+
+    # ---- VxmDense 2-D (shipped features, 64x64) and 3-D (small features, 16x16x16), bidir, fwd + bwd
+    for name, shape, feats_ in (("R2", (64, 64), [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]]),
+                                ("R3", (16, 16, 16), [[8, 16, 16], [16, 16, 16, 8, 8]])):
+        torch.manual_seed(13)
+        R = rvxm.networks.VxmDense(shape, feats_, int_steps=7, bidir=True)
+        with torch.no_grad():   # a visible deformation: the reference initialises the flow head at 1e-5
+            R.flow.weight.mul_(2e4)
+        src = t(gi.image_textured(231, 2, shape)).requires_grad_()
+        tgt = t(gi.image_textured(232, 2, shape))
+        ys, yt, flow = R(src, tgt)
+        out[f"{name}/y_source"] = ys.detach().numpy(); out[f"{name}/y_target"] = yt.detach().numpy()
+        out[f"{name}/pos_flow"] = flow.detach().numpy()
+        ys2, flow2 = R(src, tgt, registration=True)
+        assert torch.equal(flow2, flow)
+        loss = (ys * t(gi.weights(233, tuple(ys.shape), 1.0))).sum() + (yt * t(gi.weights(234, tuple(yt.shape), 1.0))).sum() \
+            + (flow * t(gi.weights(235, tuple(flow.shape), 0.1))).sum()
+        loss.backward()
+        out[f"{name}/d_src"] = src.grad.numpy()
+        out.update(sd_np(R.state_dict(), f"{name}/sd"))
+        out.update({f"{name}/grad/{k}": v.grad.numpy() for k, v in R.named_parameters()})
+    save("nets", **out)
+
+
+def gen_step():
+    """One full REGISTRATIONModel.optimize_parameters on CPU (reference code, B = 2, 64x64, ngf 8)."""
+    import_reference()
+    import shutil
+    import tempfile
+    work = tempfile.mkdtemp(prefix="dfmir_golden_")
+    shutil.copy(os.path.join(REF, "deform256.jpg"), work)
+    os.chdir(work)
+    from options.train_options import TrainOptions
+    from models import create_model
+    import models.registration_model as rm
+    B, S = 2, 64
+    opt = TrainOptions(cmd_line=f'--dataroot x --name golden --CUT_mode CUT --no_flip --gpu_ids -1 --batch_size {B} '
+                                f'--ngf 8 --crop_size {S} --load_size {S} --netF_nc 32 --num_patches 64 '
+                                f'--checkpoints_dir {work}/ckpt').parse()
+    # shim: the reference warps a batch-1 test image with a batch-B flow (registration_model.py:148-149),
+    # which F.grid_sample rejects for B > 1; hand it a batch-B image of the crop size instead.
+    dvf_img = t(gi.image_textured(301, B, (S, S), C=3))
+    rm.open_image_to_torch = lambda path, size: dvf_img
+    cnt = [0]
+    torch_randperm = torch.randperm
+    torch.randperm = det_randperm(cnt)
+    try:
+        torch.manual_seed(21)
+        m = create_model(opt)
+        data = {'A': t(gi.image_textured(302, B, (S, S))), 'B': t(gi.image_textured(303, B, (S, S))),
+                'A_paths': [], 'B_paths': []}
+        m.data_dependent_initialize(data)
+        with torch.no_grad():
+            m.netR.flow.weight.mul_(2e4)
+        m.setup(opt)
+        out = {}
+        for n in ('G', 'F', 'R'):
+            out.update(sd_np(getattr(m, 'net' + n).state_dict(), f"sd0/{n}"))
+        cnt[0] = 100      # the step's randperm draws are calls 101..115
+        m.set_input(data)
+        m.optimize_parameters()
+    finally:
+        torch.randperm = torch_randperm
+    for k, v in m.get_current_losses().items():
+        out[f"loss/{k}"] = np.float32(v)
+    for n in ('fake_B', 'idt_B', 'registered', 'regA', 'dvf'):
+        out[f"vis/{n}"] = getattr(m, n).detach().numpy()
+    for n in ('G', 'F', 'R'):
+        net = getattr(m, 'net' + n)
+        out.update({f"grad/{n}/{k}": v.grad.numpy() for k, v in net.named_parameters()})
+        out.update(sd_np(net.state_dict(), f"sd1/{n}"))
+    out["dvf_img"] = dvf_img.numpy()
+    os.chdir(ROOT)
+    save("step", **out)
+    shutil.rmtree(work, ignore_errors=True)
+
+
+SECTIONS = {"ops": gen_ops, "nets": gen_nets, "step": gen_step}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())

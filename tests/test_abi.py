@@ -11,7 +11,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 19
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.dfmir_abi_version() == 1
+    assert lib.dfmir_abi_version() == 2
 
 
 def test_no_cpu_fallback():

@@ -1,0 +1,99 @@
+"""CPU: the oracle's restatement of the networks (oracle/nets_oracle.py over the C layers) against
+golden vectors produced by the reference's own modules (oracle/gen_golden.py nets)."""
+import numpy as np
+import pytest
+
+import inputs as gi
+
+
+@pytest.fixture(scope="module")
+def nets(orc):
+    from oracle import nets_oracle
+    return nets_oracle
+
+
+def sd_of(g, prefix):
+    return {k[len(prefix) + 1:]: g[k] for k in g.files if k.startswith(prefix + "/")}
+
+
+def test_blur_layers(golden, orc):
+    g = golden("nets")
+    x = gi.weights(201, (2, 6, 12, 16), 1.0)
+    np.testing.assert_allclose(orc.blur_down(x), g["layer/down"], atol=1e-6)
+    np.testing.assert_allclose(orc.blur_up(x), g["layer/up"], atol=1e-6)
+
+
+def test_resnet_block(golden, orc):
+    g = golden("nets")
+    sd = sd_of(g, "layer/resblock_sd")
+    x = gi.weights(201, (2, 6, 12, 16), 1.0)
+    h = orc.conv(orc.pad_reflect(x, 1), sd["conv_block.1.weight"], sd["conv_block.1.bias"])
+    h = np.maximum(orc.instnorm(h), 0)
+    h = orc.conv(orc.pad_reflect(h, 1), sd["conv_block.5.weight"], sd["conv_block.5.bias"])
+    np.testing.assert_allclose(x + orc.instnorm(h), g["layer/resblock"], atol=2e-5)
+
+
+def test_resnet_generator(golden, nets):
+    g = golden("nets")
+    sd = sd_of(g, "G/sd")
+    layers = [0, 4, 8, 12, 14]
+    fake, feats = nets.resnet_generator(g["G/in"], sd, n_blocks=4, layers=layers)
+    np.testing.assert_allclose(fake, g["G/fake"], atol=5e-5)
+    for i, l in enumerate(layers):
+        ref = g[f"G/feat{i}"]
+        np.testing.assert_allclose(feats[l], ref, atol=5e-5 * max(1.0, np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("name,shape,n_enc,n_dec", [("R2", (64, 64), 6, 7), ("R3", (16, 16, 16), 3, 5)])
+def test_vxm_dense(name, shape, n_enc, n_dec, golden, nets):
+    g = golden("nets")
+    sd = sd_of(g, name + "/sd")
+    src, tgt = gi.image_textured(231, 2, shape), gi.image_textured(232, 2, shape)
+    ys, yt, flow = nets.vxm_dense(src, tgt, sd, n_enc, n_dec)
+    np.testing.assert_allclose(flow, g[name + "/pos_flow"], atol=2e-5)
+    np.testing.assert_allclose(ys, g[name + "/y_source"], atol=2e-5)
+    np.testing.assert_allclose(yt, g[name + "/y_target"], atol=2e-5)
+
+
+def test_patch_sample_and_nce(golden, orc, nets):
+    g = golden("nets")
+    sd = sd_of(g, "F/sd")
+    fq = [gi.weights(221, (2, 1, 20, 24), 1.0), gi.weights(222, (2, 16, 10, 12), 1.0)]
+    fk = [gi.weights(223, (2, 1, 20, 24), 1.0), gi.weights(224, (2, 16, 10, 12), 1.0)]
+    for i in range(2):
+        ids = g[f"F/ids{i}"]
+        # the reference's stand-in draw (gen_golden.det_randperm): call i+1 -> RandomState(9001 + i)
+        assert np.array_equal(ids, np.random.RandomState(9001 + i).permutation(fq[i].shape[2] * fq[i].shape[3])[:48])
+        q, k = nets.patch_sample(fq[i], ids, sd, i), nets.patch_sample(fk[i], ids, sd, i)
+        np.testing.assert_allclose(q, g[f"F/q{i}"], atol=2e-6)
+        np.testing.assert_allclose(k, g[f"F/k{i}"], atol=2e-6)
+        np.testing.assert_allclose(orc.patchnce(q, k, 2, 0.07), g[f"F/loss{i}"], atol=2e-5)
+
+
+def test_torch_port_step(golden, monkeypatch):
+    """oracle/torch_port.py (the CPU baseline / autograd checker) reproduces the reference's own
+    optimize_parameters: losses, visuals, every gradient, parameters after the three Adam steps."""
+    import torch
+    from oracle import torch_port as tp
+    g = golden("step")
+    torch.set_num_threads(4)
+    sds = {n: {k[len(f"sd0/{n}/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"sd0/{n}/")} for n in "GFR"}
+    st = tp.Step(sds["G"], sds["F"], sds["R"], n_blocks=9, batch_size=2, num_patches=64,
+                 dvf_image=torch.from_numpy(g["dvf_img"]))
+    cnt = [100]
+    monkeypatch.setattr(torch, "randperm", gi.det_randperm(cnt))
+    A, B = torch.from_numpy(gi.image_textured(302, 2, (64, 64))), torch.from_numpy(gi.image_textured(303, 2, (64, 64)))
+    losses = st.step(A, B)
+    for k, v in losses.items():
+        assert abs(v - float(g[f"loss/{k}"])) <= 1e-5, (k, v, float(g[f"loss/{k}"]))
+    for n, v in st.visuals.items():
+        np.testing.assert_allclose(v.detach().numpy(), g[f"vis/{n}"], atol=1e-5)
+    for n in "GFR":
+        for k, p in st.P[n].items():
+            if p.requires_grad:
+                want = g[f"grad/{n}/{k}"]
+                tol, exact_zero = gi.grad_tolerance(g, n, k, 1e-4)
+                np.testing.assert_allclose(p.grad.numpy(), want, atol=tol, err_msg=f"{n}.{k}")
+                if not exact_zero:   # Adam turns a noise gradient into a +-lr step: nothing to compare there
+                    sel = np.abs(want) > 1e-3 * np.abs(want).max()
+                    np.testing.assert_allclose(p.detach().numpy()[sel], g[f"sd1/{n}/{k}"][sel], atol=2e-5, err_msg=f"{n}.{k}")
