@@ -1,0 +1,361 @@
+// K1 (tensor-core path): 2-D stride-1 convolution as an implicit GEMM on the 5th-generation tensor
+// cores — tcgen05.mma (kind::tf32, fp32 accumulators in TMEM), operands staged in shared memory by
+// TMA, one CTA per 128-pixel x BN-channel output tile.
+//
+// Replaces the cuDNN implicit-GEMM engines behind nn.Conv2d in ResnetGenerator
+// (models/networks.py:995,1016 and the 18 ResnetBlock convs :1201,1214) for the layers whose
+// channel counts fill a tensor-core tile (Cin % 32 == 0, Cout in {64,128,256}).  The reference's
+// own CUDA path runs these in TF32 (cuDNN default); this kernel does the same arithmetic class:
+// fp32 storage, TF32 operands, fp32 accumulate.
+//
+// GEMM view per tile:  D[128 pixels][BN] = sum over (tap, 32-channel chunk) A_tap[128][32] * W_tap[BN][32]^T
+//   A_tap : the (TH x TW) pixel rectangle of the tile shifted by the tap, fetched from the
+//           channels-last activation by ONE tiled TMA box load {32 ch, TW, TH, 1}: rows land as
+//           128-byte, 128B-swizzled K-major rows — exactly the canonical UMMA operand layout; taps
+//           that reach outside the image are zero-filled by the TMA unit (zero padding for free).
+//           Reflection padding is materialised by the producer kernel (norm_resample.cu), so the
+//           ResnetBlock convs run here with pad 0 on the padded buffer.
+//   W_tap : weights pre-arranged [tap][Cout][Cin] (Cin contiguous), box {32, BN, 1}.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global, one pixel row per thread).
+// The data gradient is the same kernel run on dy with taps flipped and pad' = k-1-pad.
+#include "common.cuh"
+#include "dfmir_b200.h"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128;          // pixels per tile (UMMA M)
+constexpr int KCH = 32;          // tf32 elements per 128-byte swizzled row
+constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
+constexpr int A_BYTES = BM * 128;
+
+struct UmmaP {
+  int N, H, W;            // output sample count and spatial size
+  int Cin, Cout;
+  int KH, KW, pad_h, pad_w;
+  int TW, TH, tiles_w, tiles_h;
+  int flip;               // 1: use tap (KH*KW-1-t) of the weight tensor (data gradient)
+  int act;
+  long long ys[4];        // output element strides n, h, w, c
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 operands, both K-major
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major operand, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: D fp32, A/B tf32, K-major, M x N
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == DFMIR_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
+  if (act == DFMIR_ACT_TANH) return tanhf(v);
+  if (act == DFMIR_ACT_RELU) return v > 0.f ? v : 0.f;
+  return v;
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const float* __restrict__ bias, float* __restrict__ y, const UmmaP p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-byte aligned
+  uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
+  const int n = tile;
+  const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+  const int n0 = blockIdx.y * BN;
+  const int cchunks = p.Cin / KCH;
+  const int taps = p.KH * p.KW;
+  const int num_kb = taps * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        const int tap = kb / cchunks, cc = kb - tap * cchunks;
+        const int r = tap / p.KW, q = tap - r * p.KW;
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_expect_tx(full + s, (uint32_t)L::STAGE_BYTES);
+        tma_load_4d(sa, &tmA, full + s, cc * KCH, w0 + q - p.pad_w, h0 + r - p.pad_h, n);
+        tma_load_3d(sb, &tmB, full + s, cc * KCH, n0, p.flip ? taps - 1 - tap : tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full + s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < KCH / UMMA_K; ++k) {
+          // advance both operands by 32 bytes (8 tf32) inside the swizzled row: +2 in 16-byte units
+          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+        }
+        umma_commit(empty + s);            // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);              // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31, one output pixel per thread
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int th = row / p.TW, tw = row - th * p.TW;
+    const int oh = h0 + th, ow = w0 + tw;
+    const bool valid = oh < p.H && ow < p.W && th < p.TH;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* yp = y + (long long)n * p.ys[0] + (long long)oh * p.ys[1] + (long long)ow * p.ys[2];
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = v[j];
+          if (bias) t += __ldg(bias + n0 + c0 + j);
+          v[j] = act_apply(t, p.act);
+        }
+        if (p.ys[3] == 1) {
+          float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) yp[(long long)(n0 + c0 + j) * p.ys[3]] = v[j];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
+  if (!d) { dfmir_set_error("%s: null descriptor", who); return DFMIR_ERR_ARG; }
+  if (d->nd != 2 || d->stride != 1) { dfmir_set_error("%s: tensor-core path covers 2-D stride-1 convolutions", who); return DFMIR_ERR_UNSUPPORTED; }
+  const int Cin = dgrad ? d->Cout : d->Cin, Cout = dgrad ? d->Cin : d->Cout;
+  if (Cin % KCH || !(Cout == 64 || Cout == 128 || Cout == 256)) {
+    dfmir_set_error("%s: needs Cin %% 32 == 0 and Cout in {64,128,256} (got %d -> %d)", who, Cin, Cout);
+    return DFMIR_ERR_UNSUPPORTED;
+  }
+  p.N = d->N; p.Cin = Cin; p.Cout = Cout;
+  p.KH = d->kernel[0]; p.KW = d->kernel[1];
+  const int* osh = dgrad ? d->in_shape : d->out_shape;
+  p.H = osh[0]; p.W = osh[1];
+  p.pad_h = dgrad ? d->kernel[0] - 1 - d->pad[0] : d->pad[0];
+  p.pad_w = dgrad ? d->kernel[1] - 1 - d->pad[1] : d->pad[1];
+  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act;
+  const long long* os = dgrad ? d->x_strides : d->y_strides;
+  for (int i = 0; i < 4; ++i) p.ys[i] = os[i];
+  // tile rectangle: TW = largest power of two <= min(W,128) that keeps TH*TW = 128
+  int TW = 128;
+  while (TW > p.W && TW > 8) TW >>= 1;
+  p.TW = TW; p.TH = BM / TW;
+  p.tiles_w = (p.W + p.TW - 1) / p.TW;
+  p.tiles_h = (p.H + p.TH - 1) / p.TH;
+  return DFMIR_OK;
+}
+
+template <int BN, int STAGES>
+int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, float* y, const UmmaP& p, cudaStream_t st,
+                const char* who) {
+  using L = SmemLayout<BN, STAGES>;
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  dim3 grid((unsigned)(p.N * p.tiles_h * p.tiles_w), (unsigned)(p.Cout / BN));
+  conv_umma_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, bias, y, p);
+  DFMIR_CHECK_LAUNCH(who);
+  return DFMIR_OK;
+}
+
+// act: source activation (channels-last, element strides {n,h,w,c}, c stride 1) of spatial size (IH, IW)
+int run_umma(const float* act, const long long* as, int IH, int IW, const float* w, const float* bias, float* y,
+             const UmmaP& p, cudaStream_t st, const char* who) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
+  if (as[3] != 1 || ((uintptr_t)act & 15) || (as[0] & 3) || (as[1] & 3) || (as[2] & 3) || ((uintptr_t)w & 15)) {
+    dfmir_set_error("%s: TMA needs unit channel stride and 16-byte aligned rows", who); return DFMIR_ERR_ARG;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)as[2] * 4, (cuuint64_t)as[1] * 4, (cuuint64_t)as[0] * 4};
+    cuuint32_t box[4] = {KCH, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(activation) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  }
+  {
+    const int taps = p.KH * p.KW;
+    const int BN = p.Cout > 256 ? 256 : p.Cout;
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
+    cuuint32_t box[3] = {KCH, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  }
+  if (p.Cout == 256) return launch_umma<256, 4>(tmA, tmB, bias, y, p, st, who);
+  if (p.Cout == 128) return launch_umma<128, 3>(tmA, tmB, bias, y, p, st, who);
+  return launch_umma<64, 4>(tmA, tmB, bias, y, p, st, who);
+}
+
+}  // namespace
+
+extern "C" int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad) {
+  if (!d || d->nd != 2 || d->stride != 1) return 0;
+  const int Cin = dgrad ? d->Cout : d->Cin, Cout = dgrad ? d->Cin : d->Cout;
+  if (Cin % KCH || !(Cout == 64 || Cout == 128 || Cout == 256)) return 0;
+  const long long* is = dgrad ? d->y_strides : d->x_strides;
+  const long long* os = dgrad ? d->x_strides : d->y_strides;
+  if (is[3] != 1 || (is[0] & 3) || (is[1] & 3) || (is[2] & 3)) return 0;
+  if (os[3] == 1 && ((os[0] & 3) || (os[1] & 3) || (os[2] & 3))) return 0;
+  return 1;
+}
+
+// Forward on the tensor cores.  w: [tap][Cout][Cin] (Cin contiguous).
+extern "C" int dfmir_conv_umma_fwd(const float* x, const float* w, const float* bias, float* y,
+                                   const dfmir_conv_desc* d, void* stream) {
+  UmmaP p;
+  int rc = fill_umma(p, d, 0, "dfmir_conv_umma_fwd");
+  if (rc) return rc;
+  DFMIR_CHECK_ARG(x && w && y, "dfmir_conv_umma_fwd: null pointer");
+  return run_umma(x, d->x_strides, d->in_shape[0], d->in_shape[1], w, bias, y, p, (cudaStream_t)stream, "dfmir_conv_umma_fwd");
+}
+
+// Data gradient on the tensor cores: dx = conv(dy, flipped taps, pad' = k-1-pad).
+// w: the FORWARD layout of the fp32 path, [tap][Cin][Cout] (Cout contiguous): K-major for this product.
+extern "C" int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx, const dfmir_conv_desc* d,
+                                     void* stream) {
+  UmmaP p;
+  int rc = fill_umma(p, d, 1, "dfmir_conv_umma_dgrad");
+  if (rc) return rc;
+  DFMIR_CHECK_ARG(dy && w && dx, "dfmir_conv_umma_dgrad: null pointer");
+  return run_umma(dy, d->y_strides, d->out_shape[0], d->out_shape[1], w, nullptr, dx, p, (cudaStream_t)stream, "dfmir_conv_umma_dgrad");
+}

@@ -151,11 +151,11 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
-            wt = w.transpose(1, 2).contiguous()
             if engine == "umma":
                 from . import umma
-                _run(lambda: umma.conv_dgrad(dy, wt, dx, d), flops, True)
+                _run(lambda: umma.conv_dgrad(dy, w, dx, d), flops, True)
             else:
+                wt = w.transpose(1, 2).contiguous()
                 _run(lambda: _lib.call("dfmir_conv_dgrad", dy, wt, dx, ctypes.byref(d)), flops)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             dw = torch.zeros_like(w)

@@ -1,6 +1,29 @@
-"""tcgen05 (UMMA) convolution engine bindings: which layer shapes run on the tensor cores and the
-calls into libdfmir_b200.so for them.  Until a shape is supported here it runs on the fp32 path."""
+"""tcgen05 (UMMA) convolution engine bindings: which layer shapes run on the tensor cores
+(csrc/conv_umma.cu) and the calls into libdfmir_b200.so for them.  Everything else, and the weight
+gradient for now, runs on the fp32 CUDA-core path (csrc/conv_simt.cu)."""
+import ctypes
+
+from . import _lib
+
+_CH = (64, 128, 256)
 
 
 def supported(nd, Cin, Cout, kernel, stride, pad, x, planar_out):
-    return False
+    """Forward AND data-gradient of this layer fit the tensor-core kernel."""
+    if nd != 2 or stride != 1 or planar_out or Cin not in _CH or Cout not in _CH:
+        return False
+    st = x.stride()
+    return st[3] == 1 and all(s % 4 == 0 for s in st[:3]) and x.data_ptr() % 16 == 0
+
+
+def conv_fwd(x, w, bias, y, d):
+    wk = w.transpose(1, 2).contiguous()          # [tap][Cout][Cin]: K-major rows for the B operand
+    _lib.call("dfmir_conv_umma_fwd", x, wk, bias, y, ctypes.byref(d))
+
+
+def conv_dgrad(dy, w, dx, d):
+    _lib.call("dfmir_conv_umma_dgrad", dy, w, dx, ctypes.byref(d))   # [tap][Cin][Cout] is K-major here
+
+
+def conv_wgrad(x, dy, dw, db, d):
+    _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d))

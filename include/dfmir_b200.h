@@ -121,6 +121,12 @@ typedef struct dfmir_conv_desc {
 int dfmir_conv_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
                    void* stream);
 int dfmir_conv_dgrad(const float* dy, const float* wt, float* dx, const dfmir_conv_desc* d, void* stream);
+/* tcgen05 path (2-D, stride 1, Cin % 32 == 0, Cout in {64,128,256}; TF32 operands, fp32 accumulate in TMEM).
+ * fwd weights: [tap][Cout][Cin]; dgrad weights: [tap][Cin][Cout] (each K-major for its product). */
+int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad);
+int dfmir_conv_umma_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
+                        void* stream);
+int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx, const dfmir_conv_desc* d, void* stream);
 /* dw [tap][Cin][Cout] and db [Cout] (nullable) are accumulated into: zero-fill them first. */
 int dfmir_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d,
                      void* stream);

@@ -222,17 +222,17 @@ def test_patch_sample_and_nce_vs_reference(golden, orc, monkeypatch):
     total = 0
     for i, (q, k) in enumerate(zip(q_pool, k_pool)):
         assert np.array_equal(ids[i].cpu().numpy(), g[f"F/ids{i}"])
-        close(q, g[f"F/q{i}"], 2e-6); close(k, g[f"F/k{i}"], 2e-6)
+        close(q, g[f"F/q{i}"], 5e-6, "q"); close(k, g[f"F/k{i}"], 5e-6, "k")
         l = crit(q, k)
-        close(l, g[f"F/loss{i}"], 2e-5)
-        close(l, orc.patchnce(q.detach().cpu().numpy(), k.detach().cpu().numpy(), 2, 0.07), 2e-5)
+        close(l, g[f"F/loss{i}"], 1e-4, "loss vs reference")
+        close(l, orc.patchnce(q.detach().cpu().numpy(), k.detach().cpu().numpy(), 2, 0.07), 1e-4, "loss vs oracle")
         total = total + l.mean()
     total.backward()
-    close(fq[0].grad, g["F/dq0"], 2e-4 * np.abs(g["F/dq0"]).max())
-    close(fq[1].grad, g["F/dq1"], 2e-4 * np.abs(g["F/dq1"]).max())
+    close(fq[0].grad, g["F/dq0"], 1e-3 * np.abs(g["F/dq0"]).max(), "dq0")
+    close(fq[1].grad, g["F/dq1"], 1e-3 * np.abs(g["F/dq1"]).max(), "dq1")
     for k, p in netF.named_parameters():
         want = g[f"F/grad/{k}"]
-        close(p.grad, want, 3e-4 * max(1e-6, np.abs(want).max()), k)
+        close(p.grad, want, 1e-3 * max(1e-6, np.abs(want).max()), k)
 
 
 @pytest.mark.parametrize("name,shape,feats", [("R2", (64, 64), [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]]),
