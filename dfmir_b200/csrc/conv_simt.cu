@@ -14,6 +14,11 @@
 #include "common.cuh"
 #include "dfmir_b200.h"
 
+// direct kernels for the Cin = 1 / Cout = 1 7x7 layers (conv_thin.cu); return 1 when they handled the call
+int dfmir_thin_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d, cudaStream_t st, int* rc);
+int dfmir_thin_dgrad(const float* dy, const float* wt, float* dx, const dfmir_conv_desc* d, cudaStream_t st, int* rc);
+int dfmir_thin_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d, cudaStream_t st, int* rc);
+
 namespace {
 
 struct ConvP {
@@ -371,6 +376,8 @@ extern "C" int dfmir_conv_fwd(const float* x, const float* w, const float* bias,
   int rc = fill_geom(p, d, "dfmir_conv_fwd");
   if (rc) return rc;
   DFMIR_CHECK_ARG(x && w && y, "dfmir_conv_fwd: null pointer");
+  if (p.M == 0) return DFMIR_OK;
+  if (dfmir_thin_fwd(x, w, bias, y, d, (cudaStream_t)stream, &rc)) return rc;
   return run_conv(x, w, bias, y, p, (cudaStream_t)stream, "dfmir_conv_fwd");
 }
 
@@ -382,6 +389,8 @@ extern "C" int dfmir_conv_dgrad(const float* dy, const float* wt, float* dx, con
   int rc = fill_geom(f, d, "dfmir_conv_dgrad");
   if (rc) return rc;
   DFMIR_CHECK_ARG(dy && wt && dx, "dfmir_conv_dgrad: null pointer");
+  if (f.M == 0) return DFMIR_OK;
+  if (dfmir_thin_dgrad(dy, wt, dx, d, (cudaStream_t)stream, &rc)) return rc;
   ConvP p = f;
   p.transposed = 1; p.act = DFMIR_ACT_NONE;
   p.Cin = f.Cout; p.Cout = f.Cin;
@@ -402,6 +411,7 @@ extern "C" int dfmir_conv_wgrad(const float* x, const float* dy, float* dw, floa
   DFMIR_CHECK_ARG(x && dy && dw, "dfmir_conv_wgrad: null pointer");
   if (p.M == 0) return DFMIR_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dfmir_thin_wgrad(x, dy, dw, db, d, st, &rc)) return rc;
   constexpr int BKD = 64, BR = 16;
   const int gx = (p.K + BKD - 1) / BKD;
   auto splits_for = [&](int gy) {

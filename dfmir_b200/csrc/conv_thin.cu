@@ -1,0 +1,351 @@
+// "Thin" 2-D convolutions: the 7x7 stem (Cin = 1 -> 64, models/networks.py:983) and head (64 -> Cout = 1,
+// :1023) of ResnetGenerator, forward, data gradient and weight gradient.  Their GEMM view has N = 1 or
+// K = 49: no tensor-core tile fits, and they are bound by the one multi-channel tensor they
+// stream (0.54 GB at batch 32), so they run as direct convolutions on the CUDA cores with shared-memory
+// halo tiles and register reuse instead of as a degenerate implicit GEMM.
+//
+// Three kernels cover the six cases (s = the single-channel image, v / out = the C-channel tensor):
+//   expand : out[n,oh,ow,c] = act(b[c] + sum_tap s[n,oh+r-ph,ow+q-pw] * W[tap][c])     stem fwd, head dgrad
+//   reduce : out[n,oh,ow]   = act(b + sum_tap sum_c v[n,oh+r-ph,ow+q-pw,c] * W[tap][c]) head fwd, stem dgrad
+//   wgrad  : dW[tap][c]    += sum_p s[p+tap-(ph,pw)] * v[p][c]   (db[c] += sum_p v[p][c]) stem / head wgrad
+// Data gradients are the same correlations with flipped taps and p' = K-1-p; the head's weight gradient
+// iterates over the input domain with s = dy.  Sources are zero outside their bounds.
+#include "common.cuh"
+#include "dfmir_b200.h"
+
+namespace thin {
+
+struct ThinP {
+  int N, C, OH, OW;      // iteration domain (output pixels; for wgrad: the domain of v)
+  int SH, SW;            // spatial size of the tap-shifted source
+  int ph, pw, flip, act;
+  long long s_n, s_h, s_w;   // strides of the shifted source (single channel for expand / wgrad; v for reduce, c stride 1)
+  long long o_n, o_h, o_w;   // strides of out (expand / reduce) or of v (wgrad), c stride 1
+  int tiles_h, tiles_w;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == DFMIR_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
+  if (act == DFMIR_ACT_TANH) return tanhf(v);
+  if (act == DFMIR_ACT_RELU) return v > 0.f ? v : 0.f;
+  return v;
+}
+
+// ------------------------------------------------------------------ expand: 1 -> C channels
+// block = 32 x 8 output pixels, one pixel per thread, CT output channels in registers.
+template <int K, int CT>
+__global__ void __launch_bounds__(256)
+thin_expand_kernel(const float* __restrict__ s, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ out, const ThinP p) {
+  constexpr int TW = 32, TH = 8, SWD = TW + K - 1, SHT = TH + K - 1, TAPS = K * K;
+  __shared__ float st[SHT][SWD + 1];
+  __shared__ __align__(16) float wt[TAPS][CT];
+  int tile = blockIdx.x;
+  const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th_i = tile % p.tiles_h; const int n = tile / p.tiles_h;
+  const int h0 = th_i * TH, w0 = tw_i * TW, c0 = blockIdx.y * CT;
+  const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+  const float* sb = s + (long long)n * p.s_n;
+  for (int e = t; e < SHT * SWD; e += 256) {
+    const int r = e / SWD, c = e - r * SWD;
+    const int ih = h0 + r - p.ph, iw = w0 + c - p.pw;
+    st[r][c] = (ih >= 0 && ih < p.SH && iw >= 0 && iw < p.SW) ? __ldg(sb + ih * p.s_h + iw * p.s_w) : 0.f;
+  }
+  for (int e = t; e < TAPS * CT; e += 256) {
+    const int tp = e / CT, c = e - tp * CT;
+    wt[tp][c] = (c0 + c < p.C) ? __ldg(w + (long long)(p.flip ? TAPS - 1 - tp : tp) * p.C + c0 + c) : 0.f;
+  }
+  __syncthreads();
+  float acc[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) acc[c] = (bias && c0 + c < p.C) ? __ldg(bias + c0 + c) : 0.f;
+#pragma unroll 1
+  for (int r = 0; r < K; ++r) {
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const float sv = st[ty + r][tx + q];
+      const float4* wr = reinterpret_cast<const float4*>(wt[r * K + q]);
+#pragma unroll
+      for (int c4 = 0; c4 < CT / 4; ++c4) {
+        const float4 wv = wr[c4];
+        acc[4 * c4] = fmaf(sv, wv.x, acc[4 * c4]);
+        acc[4 * c4 + 1] = fmaf(sv, wv.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(sv, wv.z, acc[4 * c4 + 2]);
+        acc[4 * c4 + 3] = fmaf(sv, wv.w, acc[4 * c4 + 3]);
+      }
+    }
+  }
+  const int oh = h0 + ty, ow = w0 + tx;
+  if (oh >= p.OH || ow >= p.OW) return;
+  float* op = out + (long long)n * p.o_n + (long long)oh * p.o_h + (long long)ow * p.o_w + c0;
+  if (c0 + CT <= p.C && (((uintptr_t)op) & 15) == 0) {
+#pragma unroll
+    for (int c4 = 0; c4 < CT / 4; ++c4)
+      reinterpret_cast<float4*>(op)[c4] = make_float4(act_apply(acc[4 * c4], p.act), act_apply(acc[4 * c4 + 1], p.act),
+                                                      act_apply(acc[4 * c4 + 2], p.act), act_apply(acc[4 * c4 + 3], p.act));
+  } else {
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      if (c0 + c < p.C) op[c] = act_apply(acc[c], p.act);
+  }
+}
+
+// ------------------------------------------------------------------ reduce: C -> 1 channel
+// block = 32 x 32 output pixels, 4 warps; lane = column, each thread 8 vertically adjacent pixels, so a
+// column of 8+K-1 source float4s (4 channels) is loaded once per tap column and reused for 8 x K taps.
+template <int K>
+__global__ void __launch_bounds__(128)
+thin_reduce_kernel(const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ out, const ThinP p) {
+  constexpr int TW = 32, TH = 32, PH = 8, HW_ = TW + K - 1, HH = TH + K - 1, CC = 8, TAPS = K * K;
+  __shared__ float4 tile[CC / 4][HH][HW_];
+  __shared__ float4 wsm[TAPS][CC / 4];
+  int tl = blockIdx.x;
+  const int tw_i = tl % p.tiles_w; tl /= p.tiles_w;
+  const int th_i = tl % p.tiles_h; const int n = tl / p.tiles_h;
+  const int h0 = th_i * TH, w0 = tw_i * TW;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float* vb = v + (long long)n * p.s_n;
+  float acc[PH];
+#pragma unroll
+  for (int j = 0; j < PH; ++j) acc[j] = 0.f;
+  for (int c0 = 0; c0 < p.C; c0 += CC) {
+    __syncthreads();
+    for (int e = t; e < HH * HW_ * (CC / 4); e += 128) {
+      const int c4 = e % (CC / 4), px = e / (CC / 4);
+      const int row = px / HW_, col = px - row * HW_;
+      const int ih = h0 + row - p.ph, iw = w0 + col - p.pw;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ih >= 0 && ih < p.SH && iw >= 0 && iw < p.SW && c0 + c4 * 4 < p.C)
+        val = __ldg(reinterpret_cast<const float4*>(vb + ih * p.s_h + iw * p.s_w + c0 + c4 * 4));
+      tile[c4][row][col] = val;
+    }
+    for (int e = t; e < TAPS * (CC / 4); e += 128) {
+      const int tp = e / (CC / 4), c4 = e - tp * (CC / 4);
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + c4 * 4 < p.C) val = __ldg(reinterpret_cast<const float4*>(w + (long long)(p.flip ? TAPS - 1 - tp : tp) * p.C + c0 + c4 * 4));
+      wsm[tp][c4] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c4 = 0; c4 < CC / 4; ++c4) {
+#pragma unroll 1
+      for (int q = 0; q < K; ++q) {
+        float4 xs[PH + K - 1];
+#pragma unroll
+        for (int i = 0; i < PH + K - 1; ++i) xs[i] = tile[c4][warp * PH + i][lane + q];
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+          const float4 wv = wsm[r * K + q][c4];
+#pragma unroll
+          for (int j = 0; j < PH; ++j) {
+            const float4 x = xs[j + r];
+            acc[j] = fmaf(x.x, wv.x, acc[j]);
+            acc[j] = fmaf(x.y, wv.y, acc[j]);
+            acc[j] = fmaf(x.z, wv.z, acc[j]);
+            acc[j] = fmaf(x.w, wv.w, acc[j]);
+          }
+        }
+      }
+    }
+  }
+  const float b = bias ? __ldg(bias) : 0.f;
+  const int ow = w0 + lane;
+  if (ow >= p.OW) return;
+#pragma unroll
+  for (int j = 0; j < PH; ++j) {
+    const int oh = h0 + warp * PH + j;
+    if (oh < p.OH) out[(long long)n * p.o_n + (long long)oh * p.o_h + (long long)ow * p.o_w] = act_apply(acc[j] + b, p.act);
+  }
+}
+
+// ------------------------------------------------------------------ weight gradient
+// thread = (channel c, pixel group g); a unit is 8 rows x 32 columns of v's domain, group g owns 8
+// columns.  Per row the thread keeps 8 v values and, per tap row, 8+K-1 source values in registers
+// (broadcast shared-memory loads), and accumulates all K*K taps of its channel in registers.
+template <int K>
+__global__ void __launch_bounds__(256)
+thin_wgrad_kernel(const float* __restrict__ s, const float* __restrict__ v, float* __restrict__ dw, float* __restrict__ db,
+                  const ThinP p, int units) {
+  constexpr int TW = 32, TH = 8, SWD = TW + K - 1, SHT = TH + K - 1, TAPS = K * K, CT = 64, G = 4, PW = TW / G;
+  __shared__ __align__(16) float st[SHT][SWD + 2];
+  __shared__ float red[TAPS + 1][CT];
+  const int t = threadIdx.x, cl = t % CT, g = t / CT;
+  const int c = blockIdx.y * CT + cl;
+  const bool c_ok = c < p.C;
+  float acc[TAPS];
+#pragma unroll
+  for (int i = 0; i < TAPS; ++i) acc[i] = 0.f;
+  float bacc = 0.f;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    int tl = u;
+    const int tw_i = tl % p.tiles_w; tl /= p.tiles_w;
+    const int th_i = tl % p.tiles_h; const int n = tl / p.tiles_h;
+    const int h0 = th_i * TH, w0 = tw_i * TW;
+    const float* sb = s + (long long)n * p.s_n;
+    __syncthreads();
+    for (int e = t; e < SHT * SWD; e += 256) {
+      const int r = e / SWD, cc = e - r * SWD;
+      const int ih = h0 + r - p.ph, iw = w0 + cc - p.pw;
+      st[r][cc] = (ih >= 0 && ih < p.SH && iw >= 0 && iw < p.SW) ? __ldg(sb + ih * p.s_h + iw * p.s_w) : 0.f;
+    }
+    __syncthreads();
+    const float* vb = v + (long long)n * p.o_n + c;
+#pragma unroll 1
+    for (int row = 0; row < TH; ++row) {
+      const int oh = h0 + row;
+      if (oh >= p.OH) break;
+      float vv[PW];
+#pragma unroll
+      for (int j = 0; j < PW; ++j) {
+        const int ow = w0 + g * PW + j;
+        vv[j] = (c_ok && ow < p.OW) ? __ldg(vb + (long long)oh * p.o_h + (long long)ow * p.o_w) : 0.f;
+        bacc += vv[j];
+      }
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        float sr[PW + K - 1];
+#pragma unroll
+        for (int i = 0; i < PW + K - 1; ++i) sr[i] = st[row + r][g * PW + i];
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+#pragma unroll
+          for (int j = 0; j < PW; ++j) acc[r * K + q] = fmaf(sr[j + q], vv[j], acc[r * K + q]);
+      }
+    }
+  }
+  // combine the G pixel groups in shared memory, then one atomic per (tap, channel) per block
+  for (int gg = 0; gg < G; ++gg) {
+    __syncthreads();
+    if (g == gg) {
+#pragma unroll
+      for (int i = 0; i < TAPS; ++i) red[i][cl] = (gg == 0 ? 0.f : red[i][cl]) + acc[i];
+      red[TAPS][cl] = (gg == 0 ? 0.f : red[TAPS][cl]) + bacc;
+    }
+  }
+  __syncthreads();
+  for (int e = t; e < TAPS * CT; e += 256) {
+    const int tp = e / CT, cc = e - tp * CT;
+    const int ch = blockIdx.y * CT + cc;
+    if (ch < p.C) atomicAdd(dw + (long long)(p.flip ? TAPS - 1 - tp : tp) * p.C + ch, red[tp][cc]);
+  }
+  if (db && t < CT && blockIdx.y * CT + t < p.C) atomicAdd(db + blockIdx.y * CT + t, red[TAPS][t]);
+}
+
+// out[0] += sum of x[0..n)
+__global__ void __launch_bounds__(256)
+sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+  __shared__ float sm[32];
+  float a = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a += x[i];
+  a = block_sum(a, sm);
+  if (threadIdx.x == 0) atomicAdd(out, a);
+}
+
+}  // namespace thin
+
+using thin::ThinP;
+
+static bool thin_geom_ok(const dfmir_conv_desc* d) {
+  return d->nd == 2 && d->stride == 1 && d->kernel[0] == 7 && d->kernel[1] == 7 && (d->Cin == 1 || d->Cout == 1) &&
+         !(d->Cin == 1 && d->Cout == 1);
+}
+static bool vec4_ok(const float* ptr, const long long* st, int C) {   // strides {n,h,w,c}
+  return st[3] == 1 && C % 4 == 0 && (((uintptr_t)ptr) & 15) == 0 && st[0] % 4 == 0 && st[1] % 4 == 0 && st[2] % 4 == 0;
+}
+
+// Returns 1 when the call was handled (rc holds the status), 0 when the generic kernel must run.
+int dfmir_thin_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d, cudaStream_t st,
+                   int* rc) {
+  if (!thin_geom_ok(d)) return 0;
+  ThinP p{};
+  p.N = d->N; p.OH = d->out_shape[0]; p.OW = d->out_shape[1]; p.SH = d->in_shape[0]; p.SW = d->in_shape[1];
+  p.ph = d->pad[0]; p.pw = d->pad[1]; p.flip = 0; p.act = d->act;
+  p.s_n = d->x_strides[0]; p.s_h = d->x_strides[1]; p.s_w = d->x_strides[2];
+  p.o_n = d->y_strides[0]; p.o_h = d->y_strides[1]; p.o_w = d->y_strides[2];
+  if (d->Cin == 1) {
+    if (d->y_strides[3] != 1) return 0;
+    p.C = d->Cout; p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 31) / 32;
+    const unsigned gx = (unsigned)(p.N * p.tiles_h * p.tiles_w);
+    if (p.C > 16) thin::thin_expand_kernel<7, 64><<<dim3(gx, (p.C + 63) / 64), 256, 0, st>>>(x, w, bias, y, p);
+    else thin::thin_expand_kernel<7, 16><<<dim3(gx, 1), 256, 0, st>>>(x, w, bias, y, p);
+  } else {
+    if (!vec4_ok(x, d->x_strides, d->Cin) || (((uintptr_t)w) & 15)) return 0;
+    p.C = d->Cin; p.tiles_h = (p.OH + 31) / 32; p.tiles_w = (p.OW + 31) / 32;
+    thin::thin_reduce_kernel<7><<<(unsigned)(p.N * p.tiles_h * p.tiles_w), 128, 0, st>>>(x, w, bias, y, p);
+  }
+  cudaError_t e = cudaGetLastError();
+  dfmir_count_launch();
+  if (e != cudaSuccess) { dfmir_set_error("dfmir_conv_fwd(thin): launch failed: %s", cudaGetErrorString(e)); *rc = DFMIR_ERR_CUDA; }
+  else *rc = DFMIR_OK;
+  return 1;
+}
+
+// wt: [tap][Cout][Cin] (the dgrad layout of the generic path)
+int dfmir_thin_dgrad(const float* dy, const float* wt, float* dx, const dfmir_conv_desc* d, cudaStream_t st, int* rc) {
+  if (!thin_geom_ok(d)) return 0;
+  ThinP p{};
+  p.N = d->N; p.OH = d->in_shape[0]; p.OW = d->in_shape[1]; p.SH = d->out_shape[0]; p.SW = d->out_shape[1];
+  p.ph = 6 - d->pad[0]; p.pw = 6 - d->pad[1]; p.flip = 1; p.act = DFMIR_ACT_NONE;
+  p.s_n = d->y_strides[0]; p.s_h = d->y_strides[1]; p.s_w = d->y_strides[2];
+  p.o_n = d->x_strides[0]; p.o_h = d->x_strides[1]; p.o_w = d->x_strides[2];
+  if (d->Cout == 1) {        // head: dy has one channel, dx has Cin channels
+    if (d->x_strides[3] != 1) return 0;
+    p.C = d->Cin; p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 31) / 32;
+    const unsigned gx = (unsigned)(p.N * p.tiles_h * p.tiles_w);
+    if (p.C > 16) thin::thin_expand_kernel<7, 64><<<dim3(gx, (p.C + 63) / 64), 256, 0, st>>>(dy, wt, nullptr, dx, p);
+    else thin::thin_expand_kernel<7, 16><<<dim3(gx, 1), 256, 0, st>>>(dy, wt, nullptr, dx, p);
+  } else {                   // stem: dy has Cout channels, dx has one
+    if (!vec4_ok(dy, d->y_strides, d->Cout) || (((uintptr_t)wt) & 15)) return 0;
+    p.C = d->Cout; p.tiles_h = (p.OH + 31) / 32; p.tiles_w = (p.OW + 31) / 32;
+    thin::thin_reduce_kernel<7><<<(unsigned)(p.N * p.tiles_h * p.tiles_w), 128, 0, st>>>(dy, wt, nullptr, dx, p);
+  }
+  cudaError_t e = cudaGetLastError();
+  dfmir_count_launch();
+  if (e != cudaSuccess) { dfmir_set_error("dfmir_conv_dgrad(thin): launch failed: %s", cudaGetErrorString(e)); *rc = DFMIR_ERR_CUDA; }
+  else *rc = DFMIR_OK;
+  return 1;
+}
+
+int dfmir_thin_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d, cudaStream_t st,
+                     int* rc) {
+  if (!thin_geom_ok(d)) return 0;
+  ThinP p{};
+  p.N = d->N; p.act = 0;
+  const float *s, *v;
+  if (d->Cin == 1) {   // stem: s = x shifted by +tap - pad, v = dy over the output domain
+    if (d->y_strides[3] != 1) return 0;
+    s = x; v = dy; p.C = d->Cout; p.flip = 0;
+    p.OH = d->out_shape[0]; p.OW = d->out_shape[1]; p.SH = d->in_shape[0]; p.SW = d->in_shape[1];
+    p.ph = d->pad[0]; p.pw = d->pad[1];
+    p.s_n = d->x_strides[0]; p.s_h = d->x_strides[1]; p.s_w = d->x_strides[2];
+    p.o_n = d->y_strides[0]; p.o_h = d->y_strides[1]; p.o_w = d->y_strides[2];
+  } else {             // head: s = dy shifted by -tap + pad (flipped taps), v = x over the input domain
+    if (d->x_strides[3] != 1) return 0;
+    s = dy; v = x; p.C = d->Cin; p.flip = 1;
+    p.OH = d->in_shape[0]; p.OW = d->in_shape[1]; p.SH = d->out_shape[0]; p.SW = d->out_shape[1];
+    p.ph = 6 - d->pad[0]; p.pw = 6 - d->pad[1];
+    p.s_n = d->y_strides[0]; p.s_h = d->y_strides[1]; p.s_w = d->y_strides[2];
+    p.o_n = d->x_strides[0]; p.o_h = d->x_strides[1]; p.o_w = d->x_strides[2];
+  }
+  p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 31) / 32;
+  const int units = p.N * p.tiles_h * p.tiles_w;
+  const int ctiles = (p.C + 63) / 64;
+  int gx = 2 * dfmir_num_sms() / ctiles;
+  if (gx > units) gx = units;
+  if (gx < 1) gx = 1;
+  thin::thin_wgrad_kernel<7><<<dim3((unsigned)gx, (unsigned)ctiles), 256, 0, st>>>(s, v, dw, d->Cin == 1 ? db : nullptr, p, units);
+  dfmir_count_launch();
+  if (d->Cout == 1 && db) {   // bias gradient of the single output channel: sum of dy (dense (N,OH,OW,1))
+    const long long n = (long long)d->N * d->out_shape[0] * d->out_shape[1];
+    const bool dense = d->y_strides[2] == 1 && d->y_strides[1] == d->out_shape[1] &&
+                       d->y_strides[0] == (long long)d->out_shape[0] * d->out_shape[1];
+    if (!dense) { dfmir_set_error("dfmir_conv_wgrad(thin): bias gradient needs a dense dy"); *rc = DFMIR_ERR_ARG; return 1; }
+    thin::sum_kernel<<<dfmir_num_sms(), 256, 0, st>>>(dy, db, n);
+    dfmir_count_launch();
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { dfmir_set_error("dfmir_conv_wgrad(thin): launch failed: %s", cudaGetErrorString(e)); *rc = DFMIR_ERR_CUDA; }
+  else *rc = DFMIR_OK;
+  return 1;
+}

@@ -17,6 +17,7 @@ struct GemmP {
   long long sCb, sCm, sCn;
   float alpha;
   int accumulate, relu;
+  int ksplit;   // > 1: blockIdx.z = b * ksplit + slice; partial sums are combined with atomics (C pre-zeroed)
 };
 
 // C[b](m,n) (+)= alpha * sum_k A[b](m,k) B[b](k,n) (+ bias[n]) ; optional ReLU.  64x64x16 tiles, 4x4 per thread.
@@ -27,7 +28,9 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, const
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int t = threadIdx.x;
-  const int b = blockIdx.z;
+  const int b = blockIdx.z / p.ksplit, ks = blockIdx.z - b * p.ksplit;
+  const int klen = ((p.K + p.ksplit - 1) / p.ksplit + BK - 1) / BK * BK;
+  const int kbeg = ks * klen, kend = min(p.K, kbeg + klen);
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const float* Ab = A + b * p.sAb;
   const float* Bb = B + b * p.sBb;
@@ -39,14 +42,14 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, const
   const int tx = t % 16, ty = t / 16;
   // pick the load mapping that walks the contiguous axis of each operand
   const bool a_kfast = p.sAk == 1, b_nfast = p.sBn == 1;
-  for (int k0 = 0; k0 < p.K; k0 += BK) {
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int e = t + j * 256;
       int kk, mm;
       if (a_kfast) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
       const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < p.M && k < p.K) ? __ldg(Ab + m * p.sAm + k * p.sAk) : 0.f;
+      As[kk][mm] = (m < p.M && k < kend) ? __ldg(Ab + m * p.sAm + k * p.sAk) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -54,7 +57,7 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, const
       int kk, nn;
       if (b_nfast) { nn = e % BN; kk = e / BN; } else { kk = e % BK; nn = e / BK; }
       const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < p.N && k < p.K) ? __ldg(Bb + k * p.sBk + n * p.sBn) : 0.f;
+      Bs[kk][nn] = (n < p.N && k < kend) ? __ldg(Bb + k * p.sBk + n * p.sBn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -83,6 +86,7 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, const
       float v = p.alpha * acc[i][j];
       if (bias) v += __ldg(bias + n);
       float* dst = Cb + m * p.sCm + n * p.sCn;
+      if (p.ksplit > 1) { atomicAdd(dst, v); continue; }
       if (p.accumulate) v += *dst;
       if (p.relu) v = v > 0.f ? v : 0.f;
       *dst = v;
@@ -192,10 +196,23 @@ scatter_rows_kernel(const float* __restrict__ dout, const long long* __restrict_
   }
 }
 
-int launch_gemm(const float* A, const float* B, const float* bias, float* C, const GemmP& p, cudaStream_t st,
+int launch_gemm(const float* A, const float* B, const float* bias, float* C, GemmP p, cudaStream_t st,
                 const char* who) {
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return DFMIR_OK;
-  dim3 grid((p.M + 63) / 64, (p.N + 63) / 64, p.batch);
+  const int tiles = ((p.M + 63) / 64) * ((p.N + 63) / 64) * p.batch;
+  p.ksplit = 1;
+  // small outputs with a long reduction (the weight gradients of the MLP: K = B*P rows): split K over
+  // the SMs, partial sums combined with fp32 atomics into a zero-filled dense C
+  const bool dense_c = p.sCn == 1 && p.sCm == p.N && (p.batch == 1 || p.sCb == (long long)p.M * p.N);
+  if (!bias && !p.relu && dense_c && tiles < dfmir_num_sms() && p.K >= 512) {
+    int ks = (2 * dfmir_num_sms() + tiles - 1) / tiles;
+    if (ks > p.K / 128) ks = p.K / 128;
+    if (ks > 1) {
+      p.ksplit = ks;
+      if (!p.accumulate) DFMIR_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)p.batch * p.M * p.N, st));
+    }
+  }
+  dim3 grid((p.M + 63) / 64, (p.N + 63) / 64, p.batch * p.ksplit);
   gemm_simt_kernel<<<grid, 256, 0, st>>>(A, B, bias, C, p);
   DFMIR_CHECK_LAUNCH(who);
   return DFMIR_OK;
@@ -210,7 +227,7 @@ extern "C" int dfmir_gemm(const float* A, const float* B, const float* bias, flo
                           int relu, void* stream) {
   DFMIR_CHECK_ARG(A && B && C && sA && sB && sC, "dfmir_gemm: null pointer");
   DFMIR_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "dfmir_gemm: negative size");
-  GemmP p{M, N, K, batch, sA[0], sA[1], sA[2], sB[0], sB[1], sB[2], sC[0], sC[1], sC[2], alpha, accumulate, relu};
+  GemmP p{M, N, K, batch, sA[0], sA[1], sA[2], sB[0], sB[1], sB[2], sC[0], sC[1], sC[2], alpha, accumulate, relu, 1};
   return launch_gemm(A, B, bias, C, p, (cudaStream_t)stream, "dfmir_gemm");
 }
 
@@ -220,7 +237,7 @@ extern "C" int dfmir_patchnce_fwd(const float* q, const float* k, float* S, floa
   DFMIR_CHECK_ARG(q && k && S && loss, "dfmir_patchnce_fwd: null pointer");
   DFMIR_CHECK_ARG(B > 0 && P > 0 && D > 0 && T > 0.f, "dfmir_patchnce_fwd: bad sizes (B=%d P=%d D=%d T=%g)", B, P, D, T);
   cudaStream_t st = (cudaStream_t)stream;
-  GemmP p{P, P, D, B, (long long)P * D, D, 1, (long long)P * D, 1, D, (long long)P * P, P, 1, 1.0f, 0, 0};
+  GemmP p{P, P, D, B, (long long)P * D, D, 1, (long long)P * D, 1, D, (long long)P * P, P, 1, 1.0f, 0, 0, 1};
   int rc = launch_gemm(q, k, nullptr, S, p, st, "dfmir_patchnce_fwd(gemm)");
   if (rc) return rc;
   const int rows = B * P;
@@ -240,7 +257,7 @@ extern "C" int dfmir_patchnce_bwd(const float* S, const float* k, const float* g
   const long long cap = (long long)dfmir_num_sms() * 16;
   row_scale_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(S, g, work, rows, P);
   DFMIR_CHECK_LAUNCH("dfmir_patchnce_bwd(scale)");
-  GemmP p{P, D, P, B, (long long)P * P, P, 1, (long long)P * D, D, 1, (long long)P * D, D, 1, 1.0f, 0, 0};
+  GemmP p{P, D, P, B, (long long)P * P, P, 1, (long long)P * D, D, 1, (long long)P * D, D, 1, 1.0f, 0, 0, 1};
   return launch_gemm(work, k, nullptr, dq, p, st, "dfmir_patchnce_bwd(gemm)");
 }
 

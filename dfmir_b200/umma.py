@@ -26,4 +26,7 @@ def conv_dgrad(dy, w, dx, d):
 
 
 def conv_wgrad(x, dy, dw, db, d):
-    _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d))
+    if _lib.lib().dfmir_conv_umma_wgrad_supported(ctypes.byref(d)):
+        _lib.call("dfmir_conv_umma_wgrad", x, dy, dw, db, ctypes.byref(d))
+    else:
+        _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d))

@@ -127,6 +127,12 @@ int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad);
 int dfmir_conv_umma_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
                         void* stream);
 int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx, const dfmir_conv_desc* d, void* stream);
+/* tcgen05 weight gradient (2-D, stride 1, channels-last x and dy; one of Cin/Cout a multiple of 128, the other
+ * in {64,128,256k}): split-K over output pixels, TF32 operands, fp32 accumulate in TMEM, red.add into
+ * dw [tap][Cin][Cout] / db [Cout] (nullable) — both ACCUMULATED into: zero-fill them first. */
+int dfmir_conv_umma_wgrad_supported(const dfmir_conv_desc* d);
+int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d,
+                          void* stream);
 /* dw [tap][Cin][Cout] and db [Cout] (nullable) are accumulated into: zero-fill them first. */
 int dfmir_conv_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d,
                      void* stream);

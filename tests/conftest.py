@@ -13,6 +13,7 @@ for p in (ROOT, GOLD):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "tf32: run the tcgen05 (TF32 operand) convolution engine instead of the fp32 one")
 
 
 def pytest_collection_modifyitems(config, items):
