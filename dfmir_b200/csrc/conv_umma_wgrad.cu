@@ -7,8 +7,9 @@
 // GEMM view per tap: D[M][N] = A[M][K] * B[N][K]^T with K = output pixels.  Both operands are
 // channels-last activations, i.e. the channel axis (M or N) is the contiguous one: they are fed to
 // the tensor core as MN-major operands.  One TMA box {32 channels, TW, TH, 1} lands 32 pixels as 32
-// rows of 128 bytes (SWIZZLE_128B) — the canonical MN-major SW128 atom stack: 8-pixel groups 1024
-// bytes apart (SBO), 32-channel column groups PIX*128 bytes apart (LBO).  The x box is shifted by the
+// rows of 128 bytes in the one layout tcgen05 accepts for MN-major 32-bit operands
+// (SWIZZLE_128B_BASE32B = TMA's SWIZZLE_128B_ATOM_32B): 4-pixel groups 512 bytes apart (SBO),
+// 32-channel column groups PIX*128 bytes apart (LBO).  The x box is shifted by the
 // tap; pixels outside the image are zero-filled by the TMA unit (zero padding), and partial tiles
 // contribute zero because the dy box is zero-filled there.
 //
@@ -113,8 +114,8 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         mbar_wait(full + s, ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint64_t adesc = smem_desc_sw128(sa, CHUNK_BYTES, 1024);
-        const uint64_t bdesc = smem_desc_sw128(sa + L::A_BYTES, CHUNK_BYTES, 1024);
+        const uint64_t adesc = smem_desc(sa, CHUNK_BYTES, 512, LAYOUT_SW128_BASE32B);
+        const uint64_t bdesc = smem_desc(sa + L::A_BYTES, CHUNK_BYTES, 512, LAYOUT_SW128_BASE32B);
 #pragma unroll
         for (int k = 0; k < PIX / UMMA_K; ++k) {
           // next 8 pixels: +1024 bytes = +64 in 16-byte address units
@@ -241,9 +242,11 @@ extern "C" int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw,
   if (S > p.nchunks) S = p.nchunks;
 
   CUtensorMap tmX, tmG;
-  int rc = encode_act_map(&tmX, x, d->x_strides, d->Cin, d->in_shape[1], d->in_shape[0], d->N, p.TW, p.TH, who);
+  int rc = encode_act_map(&tmX, x, d->x_strides, d->Cin, d->in_shape[1], d->in_shape[0], d->N, p.TW, p.TH, who,
+                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
-  rc = encode_act_map(&tmG, dy, d->y_strides, d->Cout, d->out_shape[1], d->out_shape[0], d->N, p.TW, p.TH, who);
+  rc = encode_act_map(&tmG, dy, d->y_strides, d->Cout, d->out_shape[1], d->out_shape[0], d->N, p.TW, p.TH, who,
+                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   if (rc) return rc;
   if (BN == 256) rc = launch_wgrad<256>(tmX, tmG, dw, p, taps, S, st);
   else if (BN == 128) rc = launch_wgrad<128>(tmX, tmG, dw, p, taps, S, st);

@@ -145,6 +145,148 @@ in_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats
   }
 }
 
+// ------------------------------------------------------------------ instance norm, 128-bit path (C % 4 == 0)
+// Same arithmetic as the scalar kernels above, four channels per thread: every global access is a
+// coalesced float4, pixel coordinates come from the grid (no per-element div/mod chains).
+__device__ __forceinline__ void acc4(float* a, const float4 v) { a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w; }
+
+__global__ void __launch_bounds__(256)
+in_stats_v4_kernel(const float4* __restrict__ x, double* __restrict__ sums, int HW, int C4, int chunk) {
+  __shared__ double red[256][8];
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, npl = 256 / C4;
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (pl < npl) {
+    const float4* xb = x + (long long)n * HW * C4 + c4;
+    int px = p0 + pl;
+    while (px < p1) {
+      float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int k = 0; k < 16 && px < p1; ++k, px += npl) {
+        const float4 v = xb[(long long)px * C4];
+        fs[0] += v.x; fs[1] += v.y; fs[2] += v.z; fs[3] += v.w;
+        fq[0] = fmaf(v.x, v.x, fq[0]); fq[1] = fmaf(v.y, v.y, fq[1]); fq[2] = fmaf(v.z, v.z, fq[2]); fq[3] = fmaf(v.w, v.w, fq[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[j] += (double)fs[j]; ss[j] += (double)fq[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[threadIdx.x][2 * j] = s[j]; red[threadIdx.x][2 * j + 1] = ss[j]; }
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < npl; ++l)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[l * C4 + c4][j];
+    double* o = sums + ((long long)n * C4 * 4 + c4 * 4) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(o + j, red[threadIdx.x][j]);
+  }
+}
+
+// grid (ceil(WP*C4/256), HP, N)
+__global__ void __launch_bounds__(256)
+in_apply_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ stats, const float4* __restrict__ res,
+                   float4* __restrict__ y, int H, int W, int C4, int relu, int p, int rp) {
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= WP * C4) return;
+  const int wp = e / C4, c4 = e - wp * C4;
+  const int hp = blockIdx.y, n = blockIdx.z;
+  const int h = reflect_idx(hp - p, H), w = reflect_idx(wp - p, W);
+  const float4 s0 = __ldg(stats + ((long long)n * C4 + c4) * 2), s1 = __ldg(stats + ((long long)n * C4 + c4) * 2 + 1);
+  float4 v = x[(((long long)n * H + h) * W + w) * C4 + c4];
+  v.x = (v.x - s0.x) * s0.y; v.y = (v.y - s0.z) * s0.w; v.z = (v.z - s1.x) * s1.y; v.w = (v.w - s1.z) * s1.w;
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  if (res) {
+    const float4 r = res[(((long long)n * (H + 2 * rp) + h + rp) * (W + 2 * rp) + w + rp) * C4 + c4];
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  }
+  y[(((long long)n * HP + hp) * WP + wp) * C4 + c4] = v;
+}
+
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_v4_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ stats,
+                        float4* __restrict__ dx, float4* __restrict__ dres, double* __restrict__ sums, int H, int W, int C4,
+                        int relu, int p, int rp, int chunk) {
+  __shared__ double red[256][8];
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+  const int HP = H + 2 * p, WP = W + 2 * p;
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, npl = 256 / C4;
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (pl < npl) {
+    const float4 s0 = __ldg(stats + ((long long)n * C4 + c4) * 2), s1 = __ldg(stats + ((long long)n * C4 + c4) * 2 + 1);
+    int px = p0 + pl;
+    while (px < p1) {
+      float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < 16 && px < p1; ++k, px += npl) {
+        const int h = px / W, w = px - h * W;
+        int hl[3], wl[3];
+        const int nh = fold_list(h, H, p, hl), nw = fold_list(w, W, p, wl);
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int a = 0; a < nh; ++a)
+          for (int b = 0; b < nw; ++b) acc4(g, dy[(((long long)n * HP + hl[a]) * WP + wl[b]) * C4 + c4]);
+        const long long o = ((long long)n * HW + px) * C4 + c4;
+        if (dres) dres[(((long long)n * (H + 2 * rp) + h + rp) * (W + 2 * rp) + w + rp) * C4 + c4] = make_float4(g[0], g[1], g[2], g[3]);
+        const float4 xv = x[o];
+        const float xh[4] = {(xv.x - s0.x) * s0.y, (xv.y - s0.z) * s0.w, (xv.z - s1.x) * s1.y, (xv.w - s1.z) * s1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (relu && !(xh[j] > 0.f)) g[j] = 0.f;
+          f1[j] += g[j]; f2[j] = fmaf(g[j], xh[j], f2[j]);
+        }
+        dx[o] = make_float4(g[0], g[1], g[2], g[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[2 * j] += (double)f1[j]; s[2 * j + 1] += (double)f2[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < npl; ++l)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[l * C4 + c4][j];
+    double* o = sums + ((long long)n * C4 * 4 + c4 * 4) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(o + j, red[threadIdx.x][j]);
+  }
+}
+
+// grid (ceil(HW*C4/256), N)
+__global__ void __launch_bounds__(256)
+in_bwd_apply_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ stats, const double* __restrict__ sums,
+                       float4* __restrict__ dx, int HW, int C4) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= (long long)HW * C4) return;
+  const int n = blockIdx.y;
+  const int c4 = (int)(e % C4);
+  const long long i = (long long)n * HW * C4 + e;
+  const float4 s0 = __ldg(stats + ((long long)n * C4 + c4) * 2), s1 = __ldg(stats + ((long long)n * C4 + c4) * 2 + 1);
+  const double* sm = sums + ((long long)n * C4 * 4 + c4 * 4) * 2;
+  const double inv = 1.0 / HW;
+  const float mean[4] = {s0.x, s0.z, s1.x, s1.z}, rstd[4] = {s0.y, s0.w, s1.y, s1.w};
+  const float4 xv = x[i], gv = dx[i];
+  const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float m1 = (float)(sm[2 * j] * inv), m2 = (float)(sm[2 * j + 1] * inv);
+    const float xh = (xs[j] - mean[j]) * rstd[j];
+    r[j] = rstd[j] * (gs[j] - m1 - xh * m2);
+  }
+  dx[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+static inline bool in_v4_ok(int C, const void* a, const void* b, const void* c, const void* d) {
+  const uintptr_t m = (uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d;
+  return C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0 && (m & 15) == 0;
+}
+
 // ------------------------------------------------------------------ reflection pad (stand-alone)
 __global__ void __launch_bounds__(256)
 pad_reflect_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int p) {
@@ -382,12 +524,20 @@ extern "C" int dfmir_instnorm_fwd(const float* x, const float* res, float* y, fl
   double* sums = (double*)ws;
   DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
   int nch; const int chunk = in_chunk(H * W, N, &nch);
-  in_stats_kernel<<<dim3(nch, N), 256, 0, st>>>(x, sums, H * W, C, chunk);
+  const bool v4 = in_v4_ok(C, x, y, res, stats) && N <= 65535 && H + 2 * out_pad <= 65535;
+  if (v4) in_stats_v4_kernel<<<dim3(nch, N), 256, 0, st>>>((const float4*)x, sums, H * W, C / 4, chunk);
+  else in_stats_kernel<<<dim3(nch, N), 256, 0, st>>>(x, sums, H * W, C, chunk);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(stats)");
   in_finalize_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, stats, N * C, H * W, eps);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(finalize)");
-  const long long total = (long long)N * (H + 2 * out_pad) * (W + 2 * out_pad) * C;
-  in_apply_kernel<<<ew_grid(total), 256, 0, st>>>(x, stats, res, y, N, H, W, C, relu, out_pad, res_pad);
+  if (v4) {
+    const int HP = H + 2 * out_pad, WP = W + 2 * out_pad;
+    in_apply_v4_kernel<<<dim3((WP * (C / 4) + 255) / 256, HP, N), 256, 0, st>>>(
+        (const float4*)x, (const float4*)stats, (const float4*)res, (float4*)y, H, W, C / 4, relu, out_pad, res_pad);
+  } else {
+    const long long total = (long long)N * (H + 2 * out_pad) * (W + 2 * out_pad) * C;
+    in_apply_kernel<<<ew_grid(total), 256, 0, st>>>(x, stats, res, y, N, H, W, C, relu, out_pad, res_pad);
+  }
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(apply)");
   return DFMIR_OK;
 }
@@ -404,6 +554,16 @@ extern "C" int dfmir_instnorm_bwd(const float* dy, const float* x, const float* 
   if (dres && res_pad > 0)
     DFMIR_CUDA(cudaMemsetAsync(dres, 0, sizeof(float) * (size_t)N * (H + 2 * res_pad) * (W + 2 * res_pad) * C, st));
   int nch; const int chunk = in_chunk(H * W, N, &nch);
+  const bool v4 = in_v4_ok(C, x, dy, dx, dres) && (((uintptr_t)stats) & 15) == 0 && N <= 65535;
+  if (v4) {
+    in_bwd_reduce_v4_kernel<<<dim3(nch, N), 256, 0, st>>>((const float4*)dy, (const float4*)x, (const float4*)stats, (float4*)dx,
+                                                          (float4*)dres, sums, H, W, C / 4, relu, out_pad, res_pad, chunk);
+    DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(reduce)");
+    in_bwd_apply_v4_kernel<<<dim3((unsigned)(((long long)H * W * (C / 4) + 255) / 256), N), 256, 0, st>>>(
+        (const float4*)x, (const float4*)stats, sums, (float4*)dx, H * W, C / 4);
+    DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(apply)");
+    return DFMIR_OK;
+  }
   in_bwd_reduce_kernel<<<dim3(nch, N), 256, 0, st>>>(dy, x, stats, dx, dres, sums, H, W, C, relu, out_pad, res_pad, chunk);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(reduce)");
   in_bwd_apply_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, st>>>(x, stats, sums, dx, N, H * W, C);

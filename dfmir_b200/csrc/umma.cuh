@@ -58,20 +58,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-// Shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 //   start address [0,14) >>4, leading byte offset [16,30) >>4, stride byte offset [32,46) >>4,
-//   version [46,48) = 1 (Blackwell), layout type [61,64) = 2 (SWIZZLE_128B).
-// K-major operand (rows of 128 bytes along K): LBO unused, SBO = distance between 8-row groups.
-// MN-major operand (rows of 128 bytes along M/N, one row per K index): LBO = distance between
-// 32-element (128-byte) column groups along M/N, SBO = distance between 8-row (K) groups.
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   version [46,48) = 1 (Blackwell), layout type [61,64): 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B.
+// K-major operand, SWIZZLE_128B (rows of 128 bytes along K, 16-byte chunks XORed with row % 8): LBO
+//   unused, SBO = distance between 8-row groups.  TMA: CU_TENSOR_MAP_SWIZZLE_128B.
+// MN-major operand of a 32-bit type (tf32) has ONE legal layout, SWIZZLE_128B_BASE32B: rows of 128
+//   bytes along M/N, one row per K index, 32-byte chunks XORed with row % 4; LBO = distance between
+//   32-element (128-byte) column groups along M/N, SBO = distance between 4-row (K) groups.
+//   TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return smem_desc(saddr, lbo_bytes, sbo_bytes, LAYOUT_SW128);
 }
 // cute::UMMA::InstrDescriptor for kind::tf32: D fp32 (bits 4-5 = 1), A/B tf32 (bits 7-9, 10-12 = 2),
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at bit 17, M>>4 at bit 24.
@@ -107,6 +114,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 inline PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  // cuTensorMapEncodeTiled is a driver-API call: it needs the primary context bound to the calling
+  // thread.  Autograd worker threads may not have touched the runtime yet, so bind it once per thread.
+  static thread_local bool bound = false;
+  if (!bound) { cudaFree(0); bound = true; }
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -120,7 +131,7 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 // Tiled map over a channels-last fp32 activation (N, H, W, C) with element strides {n, h, w, 1}:
 // box = {32 channels (128 bytes, SWIZZLE_128B), box_w, box_h, 1}; out-of-bounds elements read as 0.
 inline int encode_act_map(CUtensorMap* tm, const float* act, const long long* as, int C, int W, int H, int N, int box_w,
-                          int box_h, const char* who) {
+                          int box_h, const char* who, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
   if (as[3] != 1 || ((uintptr_t)act & 15) || (as[0] & 3) || (as[1] & 3) || (as[2] & 3)) {
@@ -131,7 +142,7 @@ inline int encode_act_map(CUtensorMap* tm, const float* act, const long long* as
   cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(activation) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
   return DFMIR_OK;
 }

@@ -23,6 +23,46 @@ _BLUR3 = torch.tensor([1., 2., 1.])
 _BLUR4 = torch.tensor([1., 3., 3., 1.])
 
 
+# ---- TF32 operand emulation (for checking the tcgen05 engine) -------------------------------------
+# The tensor core reads fp32 operands and keeps sign, exponent and the top 10 mantissa bits
+# (truncation: the low 13 bits are ignored); products are exact, accumulation is fp32.  With
+# TF32_EMULATION set, the convolutions the tensor-core engine covers (2-D, stride 1, Cin and Cout in
+# {64,128,256}) run forward / data-gradient / weight-gradient on truncated operands, in the given
+# accumulation dtype.  None (default) = plain F.conv2d, the reference's CPU arithmetic.
+TF32_EMULATION = None      # None | "trunc" | "rna"
+
+
+def tf32_round(t, mode="trunc"):
+    f = t.detach().to(torch.float32).contiguous()
+    i = f.view(torch.int32)
+    if mode == "rna":       # round to nearest, ties away from zero (cvt.rna.tf32.f32)
+        i = i + 0x1000
+    i = i & ~0x1FFF
+    return i.view(torch.float32).to(t.dtype)
+
+
+class _Tf32Conv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, padding):
+        ctx.save_for_backward(x, w)
+        ctx.padding = padding
+        return F.conv2d(tf32_round(x, TF32_EMULATION), tf32_round(w, TF32_EMULATION), b, padding=padding)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gq, xq, wq = tf32_round(gy, TF32_EMULATION), tf32_round(x, TF32_EMULATION), tf32_round(w, TF32_EMULATION)
+        gx = torch.nn.grad.conv2d_input(x.shape, wq, gq, padding=ctx.padding)
+        gw = torch.nn.grad.conv2d_weight(xq, w.shape, gq, padding=ctx.padding)
+        return gx, gw, gy.sum(dim=(0, 2, 3)), None
+
+
+def conv2d(x, w, b, padding=0):
+    if TF32_EMULATION and w.shape[0] in (64, 128, 256) and w.shape[1] in (64, 128, 256):
+        return _Tf32Conv.apply(x, w, b, padding)
+    return F.conv2d(x, w, b, padding=padding)
+
+
 def _blur_filt(a, C, scale=1.0):
     f = a[:, None] * a[None, :]
     return (f / f.sum() * scale)[None, None].repeat(C, 1, 1, 1)
@@ -59,28 +99,28 @@ def resnet_generator(x, sd, n_blocks, layers=(), encode_only=False, p='model.'):
 
     try:
         a = tap(0, F.pad(x, (3,) * 4, mode='reflect'))
-        a = tap(1, F.conv2d(a, sd[p + '1.weight'], sd[p + '1.bias']))
+        a = tap(1, conv2d(a, sd[p + '1.weight'], sd[p + '1.bias']))
         a = inr(a); tap(2, a); tap(3, a)
         idx = 4
         for _ in range(2):
-            a = tap(idx, F.conv2d(a, sd[f'{p}{idx}.weight'], sd[f'{p}{idx}.bias'], padding=1))
+            a = tap(idx, conv2d(a, sd[f'{p}{idx}.weight'], sd[f'{p}{idx}.bias'], padding=1))
             a = inr(a); tap(idx + 1, a); tap(idx + 2, a)
             a = tap(idx + 3, blur_down(a))
             idx += 4
         for _ in range(n_blocks):
             q = f'{p}{idx}.conv_block.'
-            h = F.conv2d(F.pad(a, (1,) * 4, mode='reflect'), sd[q + '1.weight'], sd[q + '1.bias'])
+            h = conv2d(F.pad(a, (1,) * 4, mode='reflect'), sd[q + '1.weight'], sd[q + '1.bias'])
             h = inr(h)
-            h = F.conv2d(F.pad(h, (1,) * 4, mode='reflect'), sd[q + '5.weight'], sd[q + '5.bias'])
+            h = conv2d(F.pad(h, (1,) * 4, mode='reflect'), sd[q + '5.weight'], sd[q + '5.bias'])
             a = tap(idx, a + F.instance_norm(h))
             idx += 1
         for _ in range(2):
             a = tap(idx, blur_up(a))
-            a = tap(idx + 1, F.conv2d(a, sd[f'{p}{idx + 1}.weight'], sd[f'{p}{idx + 1}.bias'], padding=1))
+            a = tap(idx + 1, conv2d(a, sd[f'{p}{idx + 1}.weight'], sd[f'{p}{idx + 1}.bias'], padding=1))
             a = inr(a); tap(idx + 2, a); tap(idx + 3, a)
             idx += 4
         a = tap(idx, F.pad(a, (3,) * 4, mode='reflect'))
-        a = tap(idx + 1, F.conv2d(a, sd[f'{p}{idx + 1}.weight'], sd[f'{p}{idx + 1}.bias']))
+        a = tap(idx + 1, conv2d(a, sd[f'{p}{idx + 1}.weight'], sd[f'{p}{idx + 1}.bias']))
         a = tap(idx + 2, torch.tanh(a))
     except Stop:
         return feats

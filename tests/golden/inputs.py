@@ -97,6 +97,11 @@ def grad_tolerance(g, net, key, rel):
     if net == "G" and key.endswith(".bias") and not key.startswith(f"model.{last_conv}."):
         wkey = key[:-4] + "weight"
         return 2e-3 * float(np.abs(g[f"grad/{net}/{wkey}"]).max()), True
+    if net == "G" and key == f"model.{last_conv}.bias" and rel > 1e-3:
+        # sum of the output gradient over every pixel: the terms cancel to ~1e-2 of their magnitude, and the
+        # reference's own fp32 value is 5e-3 (relative) away from its fp64 value (measured with
+        # oracle/torch_port.py in both precisions); a different fp32 summation order moves it by as much.
+        rel = max(rel, 2e-2)
     return rel * max(1e-6, float(np.abs(want).max())), False
 
 

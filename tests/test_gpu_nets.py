@@ -57,6 +57,9 @@ CONV_CASES = [  # nd, N, Cin, Cout, spatial, k, stride, pad, act, planar
     (3, 1, 18, 8, (6, 8, 10), 3, 1, 1, 1, False),
     (3, 2, 8, 3, (6, 8, 10), 3, 1, 1, 0, True),
     (3, 1, 5, 7, (7, 9, 11), 3, 2, 1, 0, False),    # odd sizes, stride 2
+    (2, 2, 1, 64, (45, 76), 7, 1, 0, 0, False),     # stem at full width: several (partial) tiles of the direct kernels
+    (2, 1, 64, 1, (76, 45), 7, 1, 0, 2, False),     # head at full width
+    (2, 1, 1, 24, (40, 40), 7, 1, 3, 0, False),     # zero-padded thin conv
 ]
 
 
@@ -98,10 +101,11 @@ def test_conv_strided_views(Fn):
     close(y.permute(0, 3, 1, 2), ref, 2e-5)
 
 
+@pytest.mark.parametrize("C", [12, 16, 64])       # 12: scalar kernels; 16 / 64: the 128-bit kernels
 @pytest.mark.parametrize("relu,pad,with_res", [(True, 0, False), (True, 1, False), (True, 3, False), (False, 1, True), (False, 0, True)])
-def test_instnorm_fused(relu, pad, with_res, Fn):
+def test_instnorm_fused(relu, pad, with_res, C, Fn):
     r = gi.rng(600 + pad)
-    N, C, H, W = 2, 12, 10, 14
+    N, H, W = 2, 10, 14
     x = torch.from_numpy((r.standard_normal((N, C, H, W)) * 2 + 0.5).astype(np.float32)).requires_grad_()
     res = torch.from_numpy(r.standard_normal((N, C, H, W)).astype(np.float32)).requires_grad_() if with_res else None
     y = F.instance_norm(x, eps=1e-5)
