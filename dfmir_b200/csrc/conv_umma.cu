@@ -1,23 +1,30 @@
 // K1 (tensor-core path): 2-D stride-1 convolution as an implicit GEMM on the 5th-generation tensor
 // cores — tcgen05.mma (kind::tf32, fp32 accumulators in TMEM), operands staged in shared memory by
-// TMA, one CTA per 128-pixel x BN-channel output tile.
+// TMA, persistent CTAs (one per SM) that each walk a list of output tiles.
 //
 // Replaces the cuDNN implicit-GEMM engines behind nn.Conv2d in ResnetGenerator
 // (models/networks.py:995,1016 and the 18 ResnetBlock convs :1201,1214) for the layers whose
 // channel counts fill a tensor-core tile (Cin % 32 == 0, Cout in {64,128,256}).  The reference's
 // own CUDA path runs these in TF32 (cuDNN default); this kernel does the same arithmetic class:
-// fp32 storage, TF32 operands, fp32 accumulate.
+// fp32 storage, TF32 operands (the tensor core truncates fp32 to 10 mantissa bits), fp32 accumulate.
 //
-// GEMM view per tile:  D[128 pixels][BN] = sum over (tap, 32-channel chunk) A_tap[128][32] * W_tap[BN][32]^T
-//   A_tap : the (TH x TW) pixel rectangle of the tile shifted by the tap, fetched from the
+// GEMM view per work item: MT sub-tiles of 128 pixels x BN output channels,
+//     D_j[128][BN] = sum over (tap, 32-channel chunk) A_j,tap[128][32] * W_tap[BN][32]^T ,  j < MT
+//   A_j,tap : the (TH x TW) pixel rectangle of sub-tile j shifted by the tap, fetched from the
 //           channels-last activation by ONE tiled TMA box load {32 ch, TW, TH, 1}: rows land as
-//           128-byte, 128B-swizzled K-major rows — exactly the canonical UMMA operand layout; taps
-//           that reach outside the image are zero-filled by the TMA unit (zero padding for free).
+//           128-byte, 128B-swizzled K-major rows — the canonical UMMA operand layout; taps that
+//           reach outside the image are zero-filled by the TMA unit (zero padding for free).
 //           Reflection padding is materialised by the producer kernel (norm_resample.cu), so the
 //           ResnetBlock convs run here with pad 0 on the padded buffer.
-//   W_tap : weights pre-arranged [tap][Cout][Cin] (Cin contiguous), box {32, BN, 1}.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global, one pixel row per thread).
+//   W_tap : weights pre-arranged [tap][Cout][Cin] (Cin contiguous), box {32, BN, 1}; ONE weight
+//           tile per pipeline stage feeds all MT sub-tiles, which is what keeps the operand
+//           stream (L2 -> shared memory, the binding resource for 4-byte TF32 operands) below
+//           the tensor pipe's appetite: (MT*16 + BN/8) KB per MT*4 MMAs.
+// TMEM: MT*BN accumulator columns per stage, AS stages (512 columns in all): with AS = 2 the
+// epilogue of one work item overlaps the MMAs of the next.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = epilogue (TMEM -> registers -> bias/activation -> global, one pixel row per thread;
+// two warps share each TMEM lane quarter and split the sub-tiles).
 // The data gradient is the same kernel run on dy with taps flipped and pad' = k-1-pad.
 #include "umma.cuh"
 #include "dfmir_b200.h"
@@ -25,16 +32,19 @@
 namespace {
 using namespace umma;
 
-constexpr int BM = 128;          // pixels per tile (UMMA M)
+constexpr int BM = 128;          // pixels per sub-tile (UMMA M)
 constexpr int KCH = 32;          // tf32 elements per 128-byte swizzled row
 constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
 constexpr int A_BYTES = BM * 128;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 struct UmmaP {
   int N, H, W;            // output sample count and spatial size
   int Cin, Cout;
   int KH, KW, pad_h, pad_w;
   int TW, TH, tiles_w, tiles_h;
+  int ptiles;             // N * tiles_h * tiles_w sub-tiles of 128 pixels
   int flip;               // 1: use tap (KH*KW-1-t) of the weight tensor (data gradient)
   int act;
   long long ys[4];        // output element strides n, h, w, c
@@ -47,128 +57,165 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-template <int BN, int STAGES>
+template <int BN, int MT, int STAGES, int AS>
 struct SmemLayout {
+  static_assert(MT * BN * AS <= 512, "TMEM has 512 columns");
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int NBARS = 2 * STAGES + 2 * AS;
+  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192)
+template <int BN, int MT, int STAGES, int AS>
+__global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ bias, float* __restrict__ y, const UmmaP p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, MT, STAGES, AS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-byte aligned
   uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_empty = tmem_full + AS;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + AS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  int tile = blockIdx.x;
-  const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
-  const int n = tile;
-  const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
-  const int n0 = blockIdx.y * BN;
+  const int n_tiles = p.Cout / BN;
+  const int pgroups = (p.ptiles + MT - 1) / MT;
+  const int items = pgroups * n_tiles;
   const int cchunks = p.Cin / KCH;
   const int taps = p.KH * p.KW;
   const int num_kb = taps * cchunks;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int a = 0; a < AS; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, EPI_WARPS); }
+    fence_barrier_init();
   }
-  if (warp == 1) {   // TMEM: BN fp32 accumulator columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(empty + s, ph ^ 1);
-        const int tap = kb / cchunks, cc = kb - tap * cchunks;
-        const int r = tap / p.KW, q = tap - r * p.KW;
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        mbar_expect_tx(full + s, (uint32_t)L::STAGE_BYTES);
-        tma_load_4d(sa, &tmA, full + s, cc * KCH, w0 + q - p.pad_w, h0 + r - p.pad_h, n);
-        tma_load_3d(sb, &tmB, full + s, cc * KCH, n0, p.flip ? taps - 1 - tap : tap);
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int nt = item % n_tiles, pg = item / n_tiles;
+        int sn[MT], sh[MT], sw[MT];
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int pt = pg * MT + j;
+          if (pt < p.ptiles) {
+            const int n = pt / tiles_per_img, rem = pt - n * tiles_per_img;
+            const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+            sn[j] = n; sh[j] = th_i * p.TH; sw[j] = tw_i * p.TW;
+          } else { sn[j] = p.N; sh[j] = 0; sw[j] = 0; }      // beyond the batch: the TMA unit zero-fills
+        }
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          const int tap = kb / cchunks, cc = kb - tap * cchunks;
+          const int r = tap / p.KW, q = tap - r * p.KW;
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          mbar_expect_tx(full + s, (uint32_t)L::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            tma_load_4d(sa + j * A_BYTES, &tmA, full + s, cc * KCH, sw[j] + q - p.pad_w, sh[j] + r - p.pad_h, sn[j]);
+          tma_load_3d(sa + MT * A_BYTES, &tmB, full + s, cc * KCH, nt * BN, p.flip ? taps - 1 - tap : tap);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer
       constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(full + s, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint64_t adesc = smem_desc_sw128(sa, 16, 1024), bdesc = smem_desc_sw128(sa + A_BYTES, 16, 1024);
+      uint32_t it = 0, ti = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+        const uint32_t as = ti % AS, aph = (ti / AS) & 1;
+        mbar_wait(tmem_empty + as, aph ^ 1);        // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * (MT * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t bdesc = smem_desc_sw128(sa + MT * A_BYTES, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < KCH / UMMA_K; ++k) {
-          // advance both operands by 32 bytes (8 tf32) inside the swizzled row: +2 in 16-byte units
-          umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          for (int j = 0; j < MT; ++j) {
+            const uint64_t adesc = smem_desc_sw128(sa + j * A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < KCH / UMMA_K; ++k) {
+              // advance both operands by 32 bytes (8 tf32) inside the swizzled row: +2 in 16-byte units
+              umma_tf32(acc + j * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
+          }
+          umma_commit(empty + s);            // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty + s);            // frees the smem stage when these MMAs retire
+        umma_commit(tmem_full + as);         // accumulators of this work item complete
       }
-      umma_commit(tmem_full);              // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31, one output pixel per thread
-    const int quarter = warp & 3;
+    // ---------------- epilogue: warp e reads TMEM lanes 32*(e%4) .. +31 of sub-tiles e/4, e/4 + 2, ...
+    const int e = warp - 2;
+    const int quarter = warp & 3;            // hardware rule: a warp may access TMEM lanes 32*(warp%4)..+31
+    const int jfirst = e >> 2;
     const int row = quarter * 32 + lane;
     const int th = row / p.TW, tw = row - th * p.TW;
-    const int oh = h0 + th, ow = w0 + tw;
-    const bool valid = oh < p.H && ow < p.W && th < p.TH;
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* yp = y + (long long)n * p.ys[0] + (long long)oh * p.ys[1] + (long long)ow * p.ys[2];
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+      const uint32_t as = ti % AS, aph = (ti / AS) & 1;
+      const int nt = item % n_tiles, pg = item / n_tiles;
+      const int n0 = nt * BN;
+      mbar_wait(tmem_full + as, aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      if (valid) {
+      for (int j = jfirst; j < MT; j += EPI_WARPS / 4) {
+        const int pt = pg * MT + j;
+        const int n = pt / tiles_per_img, rem = pt - n * tiles_per_img;
+        const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        const int oh = th_i * p.TH + th, ow = tw_i * p.TW + tw;
+        const bool valid = pt < p.ptiles && oh < p.H && ow < p.W;
+        float* yp = y + (long long)n * p.ys[0] + (long long)oh * p.ys[1] + (long long)ow * p.ys[2];
+        const uint32_t acc = tmem_base + as * (MT * BN) + j * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(acc + (uint32_t)c0, v);
+          if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = v[j];
-          if (bias) t += __ldg(bias + n0 + c0 + j);
-          v[j] = act_apply(t, p.act);
-        }
-        if (p.ys[3] == 1) {
-          float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
+            for (int i = 0; i < 32; ++i) {
+              float t = v[i];
+              if (bias) t += __ldg(bias + n0 + c0 + i);
+              v[i] = act_apply(t, p.act);
+            }
+            if (p.ys[3] == 1) {
+              float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) yp[(long long)(n0 + c0 + j) * p.ys[3]] = v[j];
+              for (int i = 0; i < 32; ++i) yp[(long long)(n0 + c0 + i) * p.ys[3]] = v[i];
+            }
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
-  }
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
 // ---------------------------------------------------------------- host side
@@ -195,16 +242,24 @@ int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
   p.TW = TW; p.TH = BM / TW;
   p.tiles_w = (p.W + p.TW - 1) / p.TW;
   p.tiles_h = (p.H + p.TH - 1) / p.TH;
+  p.ptiles = p.N * p.tiles_h * p.tiles_w;
   return DFMIR_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int MT, int STAGES, int AS>
 int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bias, float* y, const UmmaP& p, cudaStream_t st,
                 const char* who) {
-  using L = SmemLayout<BN, STAGES>;
-  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-  dim3 grid((unsigned)(p.N * p.tiles_h * p.tiles_w), (unsigned)(p.Cout / BN));
-  conv_umma_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, bias, y, p);
+  using L = SmemLayout<BN, MT, STAGES, AS>;
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, MT, STAGES, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  const int items = ((p.ptiles + MT - 1) / MT) * (p.Cout / BN);
+  if (items == 0) return DFMIR_OK;
+  // persistent CTAs, one per SM; with fewer items than SMs every item gets its own CTA
+  int grid = dfmir_num_sms();
+  if (grid > items) grid = items;
+  // balance: the same number of rounds on every CTA that runs (e.g. 256 items -> 128 CTAs x 2)
+  const int rounds = (items + grid - 1) / grid;
+  grid = (items + rounds - 1) / rounds;
+  conv_umma_kernel<BN, MT, STAGES, AS><<<grid, THREADS, L::TOTAL, st>>>(tmA, tmB, bias, y, p);
   DFMIR_CHECK_LAUNCH(who);
   return DFMIR_OK;
 }
@@ -238,9 +293,9 @@ int run_umma(const float* act, const long long* as, int IH, int IW, const float*
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
   }
-  if (p.Cout == 256) return launch_umma<256, 4>(tmA, tmB, bias, y, p, st, who);
-  if (p.Cout == 128) return launch_umma<128, 3>(tmA, tmB, bias, y, p, st, who);
-  return launch_umma<64, 4>(tmA, tmB, bias, y, p, st, who);
+  if (p.Cout == 256) return launch_umma<256, 2, 3, 1>(tmA, tmB, bias, y, p, st, who);
+  if (p.Cout == 128) return launch_umma<128, 2, 4, 2>(tmA, tmB, bias, y, p, st, who);
+  return launch_umma<64, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
 }
 
 }  // namespace

@@ -321,9 +321,21 @@ pad_reflect_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int
   }
 }
 
-// ------------------------------------------------------------------ blur-pool down (x0.5)
+// ------------------------------------------------------------------ blur-pool down (x0.5) / blur-up (x2)
+// Templated on the element type: float4 (four channels per thread, 128-bit accesses) when C % 4 == 0,
+// float otherwise.  Adjoint tap lists live in three fixed register slots per axis (weight 0 = unused).
+struct V1 { typedef float T; };
+__device__ __forceinline__ float vzero(float) { return 0.f; }
+__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vfma(float& a, const float x, const float w) { a = fmaf(x, w, a); }
+__device__ __forceinline__ void vfma(float4& a, const float4 x, const float w) {
+  a.x = fmaf(x.x, w, a.x); a.y = fmaf(x.y, w, a.y); a.z = fmaf(x.z, w, a.z); a.w = fmaf(x.w, w, a.w);
+}
+struct Adj3 { int o[3]; float w[3]; };
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-blur_down_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int OH, int OW) {
+blur_down_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW) {
   const long long total = (long long)N * OH * OW * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long q = i;
@@ -331,8 +343,8 @@ blur_down_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, 
     const int ow = (int)(q % OW); q /= OW;
     const int oh = (int)(q % OH); q /= OH;
     const int n = (int)q;
-    const float* xb = x + (long long)n * H * W * C + c;
-    float acc = 0.f;
+    const T* xb = x + (long long)n * H * W * C + c;
+    T acc = vzero(T());
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const int h = reflect_idx(2 * oh - 1 + a, H);
@@ -341,36 +353,32 @@ blur_down_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, 
       for (int b = 0; b < 3; ++b) {
         const int w = reflect_idx(2 * ow - 1 + b, W);
         const float fb = b == 1 ? 0.5f : 0.25f;
-        acc += xb[((long long)h * W + w) * C] * (fa * fb);
+        vfma(acc, xb[((long long)h * W + w) * C], fa * fb);
       }
     }
     y[i] = acc;
   }
 }
 
-// adjoint taps of the blur-pool along one axis: list of (o, weight) that read input index h
-__device__ __forceinline__ int blur_down_adj(int h, int H, int OH, int* o, float* wt) {
-  int n = 0;
-  int cand[3]; int nc = 0;
-  cand[nc++] = h;
-  if (h == 1) cand[nc++] = -1;
-  if (h == H - 2) cand[nc++] = H;
-  for (int k = 0; k < nc; ++k) {
-    const int hp = cand[k];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int num = hp + 1 - a;
-      if (num < 0 || (num & 1)) continue;
-      const int oo = num >> 1;
-      if (oo >= OH) continue;
-      o[n] = oo; wt[n] = a == 1 ? 0.5f : 0.25f; ++n;
-    }
+// adjoint taps of the blur-pool along one axis: outputs o (weight w) that read input index h.
+//   direct: 2o-1+a = h;  reflected: index -1 aliases 1 (o = 0, a = 0), index H aliases H-2 (H odd: o = OH-1, a = 2)
+__device__ __forceinline__ Adj3 blur_down_adj(int h, int H, int OH) {
+  Adj3 r;
+  r.o[0] = r.o[1] = r.o[2] = 0; r.w[0] = r.w[1] = r.w[2] = 0.f;
+  if ((h & 1) == 0) {
+    if (h / 2 < OH) { r.o[0] = h / 2; r.w[0] = 0.5f; }
+  } else {
+    r.o[0] = (h - 1) / 2; r.w[0] = 0.25f;
+    if ((h + 1) / 2 < OH) { r.o[1] = (h + 1) / 2; r.w[1] = 0.25f; }
   }
-  return n;
+  if (h == 1) { r.o[2] = 0; r.w[2] = 0.25f; }
+  else if (h == H - 2 && (H & 1)) { r.o[2] = OH - 1; r.w[2] = 0.25f; }
+  return r;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-blur_down_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
+blur_down_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
   const long long total = (long long)N * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long q = i;
@@ -378,20 +386,24 @@ blur_down_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N
     const int w = (int)(q % W); q /= W;
     const int h = (int)(q % H); q /= H;
     const int n = (int)q;
-    int oh[6], ow[6]; float fh[6], fw[6];
-    const int nh = blur_down_adj(h, H, OH, oh, fh), nw = blur_down_adj(w, W, OW, ow, fw);
-    const float* gb = dy + (long long)n * OH * OW * C + c;
-    float acc = 0.f;
-    for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b) acc += gb[((long long)oh[a] * OW + ow[b]) * C] * (fh[a] * fw[b]);
+    const Adj3 ah = blur_down_adj(h, H, OH), aw = blur_down_adj(w, W, OW);
+    const T* gb = dy + (long long)n * OH * OW * C + c;
+    T acc = vzero(T());
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (ah.w[a] == 0.f) continue;
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        if (aw.w[b] != 0.f) vfma(acc, gb[((long long)ah.o[a] * OW + aw.o[b]) * C], ah.w[a] * aw.w[b]);
+    }
     dx[i] = acc;
   }
 }
 
-// ------------------------------------------------------------------ blur-up (x2)
 // per axis: y[2m] = (x[clamp(m-1)] + 3 x[m]) / 4 ; y[2m+1] = (3 x[m] + x[clamp(m+1)]) / 4
+template <typename T>
 __global__ void __launch_bounds__(256)
-blur_up_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
+blur_up_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
   const int OH = 2 * H, OW = 2 * W;
   const long long total = (long long)N * OH * OW * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -405,23 +417,32 @@ blur_up_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, in
     const int w0 = (ow & 1) ? mw : max(mw - 1, 0), w1 = (ow & 1) ? min(mw + 1, W - 1) : mw;
     const float fh0 = (oh & 1) ? 0.75f : 0.25f, fh1 = 1.f - fh0;
     const float fw0 = (ow & 1) ? 0.75f : 0.25f, fw1 = 1.f - fw0;
-    const float* xb = x + (long long)n * H * W * C + c;
-    y[i] = fh0 * (fw0 * xb[((long long)h0 * W + w0) * C] + fw1 * xb[((long long)h0 * W + w1) * C]) +
-           fh1 * (fw0 * xb[((long long)h1 * W + w0) * C] + fw1 * xb[((long long)h1 * W + w1) * C]);
+    const T* xb = x + (long long)n * H * W * C + c;
+    // same association as the scalar formula: fh0 * (fw0 a + fw1 b) + fh1 * (fw0 c + fw1 d)
+    T r0 = vzero(T()), r1 = vzero(T()), acc = vzero(T());
+    vfma(r0, xb[((long long)h0 * W + w0) * C], fw0); vfma(r0, xb[((long long)h0 * W + w1) * C], fw1);
+    vfma(r1, xb[((long long)h1 * W + w0) * C], fw0); vfma(r1, xb[((long long)h1 * W + w1) * C], fw1);
+    vfma(acc, r0, fh0); vfma(acc, r1, fh1);
+    y[i] = acc;
   }
 }
 
-__device__ __forceinline__ int blur_up_adj(int m, int H, int* o, float* wt) {
-  int n = 0;
-  o[n] = 2 * m; wt[n++] = 0.75f;
-  o[n] = 2 * m + 1; wt[n++] = 0.75f;
-  if (m + 1 <= H - 1) { o[n] = 2 * m + 2; wt[n++] = 0.25f; } else { o[n] = 2 * m + 1; wt[n++] = 0.25f; }  // clamp(m+1)
-  if (m - 1 >= 0) { o[n] = 2 * m - 1; wt[n++] = 0.25f; } else { o[n] = 2 * m; wt[n++] = 0.25f; }          // clamp(m-1)
-  return n;
+// adjoint of the blur-up along one axis: outputs that read input m.  2m and 2m+1 (weight 3/4 each);
+// 2m+2 reads x[m] as clamp(m+1-1)... i.e. y[2(m+1)] uses x[m] with 1/4 (if m+1 < H, else the clamp makes
+// y[2m+1] read x[m] twice); y[2(m-1)+1] = y[2m-1] uses x[m] with 1/4 (if m > 0, else y[2m] reads it twice).
+struct Adj4 { int o[4]; float w[4]; };
+__device__ __forceinline__ Adj4 blur_up_adj(int m, int H) {
+  Adj4 r;
+  r.o[0] = 2 * m; r.w[0] = 0.75f;
+  r.o[1] = 2 * m + 1; r.w[1] = 0.75f;
+  r.o[2] = (m + 1 <= H - 1) ? 2 * m + 2 : 2 * m + 1; r.w[2] = 0.25f;
+  r.o[3] = (m - 1 >= 0) ? 2 * m - 1 : 2 * m; r.w[3] = 0.25f;
+  return r;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-blur_up_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C) {
+blur_up_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C) {
   const int OW = 2 * W, OH = 2 * H;
   const long long total = (long long)N * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -430,12 +451,13 @@ blur_up_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, 
     const int w = (int)(q % W); q /= W;
     const int h = (int)(q % H); q /= H;
     const int n = (int)q;
-    int oh[4], ow[4]; float fh[4], fw[4];
-    const int nh = blur_up_adj(h, H, oh, fh), nw = blur_up_adj(w, W, ow, fw);
-    const float* gb = dy + (long long)n * OH * OW * C + c;
-    float acc = 0.f;
-    for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b) acc += gb[((long long)oh[a] * OW + ow[b]) * C] * (fh[a] * fw[b]);
+    const Adj4 ah = blur_up_adj(h, H), aw = blur_up_adj(w, W);
+    const T* gb = dy + (long long)n * OH * OW * C + c;
+    T acc = vzero(T());
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) vfma(acc, gb[((long long)ah.o[a] * OW + aw.o[b]) * C], ah.w[a] * aw.w[b]);
     dx[i] = acc;
   }
 }
@@ -591,7 +613,11 @@ extern "C" int dfmir_pad_reflect_bwd(const float* dy, float* dx, int N, int H, i
 extern "C" int dfmir_blur_down_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
   DFMIR_CHECK_ARG(x && y && N > 0 && H > 1 && W > 1 && C > 0, "dfmir_blur_down_fwd: bad argument");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  blur_down_fwd_kernel<<<ew_grid((long long)N * OH * OW * C), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C, OH, OW);
+  if (C % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0)
+    blur_down_fwd_kernel<float4><<<ew_grid((long long)N * OH * OW * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, (float4*)y, N, H, W, C / 4, OH, OW);
+  else
+    blur_down_fwd_kernel<float><<<ew_grid((long long)N * OH * OW * C), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C, OH, OW);
   DFMIR_CHECK_LAUNCH("dfmir_blur_down_fwd");
   return DFMIR_OK;
 }
@@ -599,21 +625,33 @@ extern "C" int dfmir_blur_down_fwd(const float* x, float* y, int N, int H, int W
 extern "C" int dfmir_blur_down_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
   DFMIR_CHECK_ARG(dy && dx && N > 0 && H > 1 && W > 1 && C > 0, "dfmir_blur_down_bwd: bad argument");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  blur_down_bwd_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C, OH, OW);
+  if (C % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0)
+    blur_down_bwd_kernel<float4><<<ew_grid((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dy, (float4*)dx, N, H, W, C / 4, OH, OW);
+  else
+    blur_down_bwd_kernel<float><<<ew_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C, OH, OW);
   DFMIR_CHECK_LAUNCH("dfmir_blur_down_bwd");
   return DFMIR_OK;
 }
 
 extern "C" int dfmir_blur_up_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream) {
   DFMIR_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "dfmir_blur_up_fwd: bad argument");
-  blur_up_fwd_kernel<<<ew_grid((long long)N * 4 * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C);
+  if (C % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0)
+    blur_up_fwd_kernel<float4><<<ew_grid((long long)N * 4 * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, (float4*)y, N, H, W, C / 4);
+  else
+    blur_up_fwd_kernel<float><<<ew_grid((long long)N * 4 * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, y, N, H, W, C);
   DFMIR_CHECK_LAUNCH("dfmir_blur_up_fwd");
   return DFMIR_OK;
 }
 
 extern "C" int dfmir_blur_up_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
   DFMIR_CHECK_ARG(dy && dx && N > 0 && H > 0 && W > 0 && C > 0, "dfmir_blur_up_bwd: bad argument");
-  blur_up_bwd_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C);
+  if (C % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0)
+    blur_up_bwd_kernel<float4><<<ew_grid((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dy, (float4*)dx, N, H, W, C / 4);
+  else
+    blur_up_bwd_kernel<float><<<ew_grid((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C);
   DFMIR_CHECK_LAUNCH("dfmir_blur_up_bwd");
   return DFMIR_OK;
 }

@@ -362,3 +362,21 @@ def test_training_step_tensor_core_engine(golden, monkeypatch):
             tol, _ = gi.grad_tolerance(g, n, k, 3e-2)
             err = float(np.abs(p.grad.cpu().numpy() - want).max())
             assert err <= tol, (n, k, err, tol)
+
+
+@pytest.mark.parametrize("C,H,W", [(8, 12, 16), (16, 9, 11)])
+def test_blur_layers_128bit_path(C, H, W, Fn):
+    """Downsample / Upsample (anti-aliased) on the float4 kernels (C % 4 == 0), odd and even sizes, against the
+    torch CPU port of the reference layers (oracle/torch_port.py blur_down / blur_up) with autograd."""
+    from oracle import torch_port as tp
+    r = gi.rng(800 + C)
+    for name, ref_fn, fn in (("down", tp.blur_down, Fn.blur_down_cl), ("up", tp.blur_up, Fn.blur_up_cl)):
+        x = torch.from_numpy(r.standard_normal((2, C, H, W)).astype(np.float32)).requires_grad_()
+        y = ref_fn(x)
+        gy = torch.from_numpy(r.standard_normal(tuple(y.shape)).astype(np.float32))
+        y.backward(gy)
+        xg = x.detach().cuda().permute(0, 2, 3, 1).contiguous().requires_grad_()
+        yg = fn(xg)
+        close(yg.permute(0, 3, 1, 2), y, 2e-6, name)
+        yg.backward(gy.cuda().permute(0, 2, 3, 1).contiguous())
+        close(xg.grad.permute(0, 3, 1, 2), x.grad, 4e-6, name + " bwd")
