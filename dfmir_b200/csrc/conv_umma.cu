@@ -28,6 +28,7 @@
 // The data gradient is the same kernel run on dy with taps flipped and pad' = k-1-pad.
 #include "umma.cuh"
 #include "dfmir_b200.h"
+#include <stdlib.h>
 
 namespace {
 using namespace umma;
@@ -236,10 +237,15 @@ int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
   p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act;
   const long long* os = dgrad ? d->x_strides : d->y_strides;
   for (int i = 0; i < 4; ++i) p.ys[i] = os[i];
-  // tile rectangle: TW = largest power of two <= min(W,128) that keeps TH*TW = 128
-  int TW = 128;
-  while (TW > p.W && TW > 8) TW >>= 1;
-  p.TW = TW; p.TH = BM / TW;
+  // tile rectangle TH x TW = 128 pixels (powers of two, TW >= 8): the shape that wastes the fewest
+  // pixels on partial tiles (66x66 data-gradient outputs: 16x8 covers 76 % vs 52 % for 64x2); ties go to
+  // the widest tile (longest contiguous runs per TMA box row)
+  long long best = -1;
+  for (int TW = 128; TW >= 8; TW >>= 1) {
+    const int TH = BM / TW;
+    const long long area = (long long)((p.W + TW - 1) / TW) * TW * ((p.H + TH - 1) / TH) * TH;
+    if (best < 0 || area < best) { best = area; p.TW = TW; p.TH = TH; }
+  }
   p.tiles_w = (p.W + p.TW - 1) / p.TW;
   p.tiles_h = (p.H + p.TH - 1) / p.TH;
   p.ptiles = p.N * p.tiles_h * p.tiles_w;
@@ -267,6 +273,7 @@ int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
 // act: source activation (channels-last, element strides {n,h,w,c}, c stride 1) of spatial size (IH, IW)
 int run_umma(const float* act, const long long* as, int IH, int IW, const float* w, const float* bias, float* y,
              const UmmaP& p, cudaStream_t st, const char* who) {
+  static const int cfg = getenv("DFMIR_UMMA_CFG") ? atoi(getenv("DFMIR_UMMA_CFG")) : 0;   // tuning experiments
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
   if (as[3] != 1 || ((uintptr_t)act & 15) || (as[0] & 3) || (as[1] & 3) || (as[2] & 3) || ((uintptr_t)w & 15)) {
@@ -284,7 +291,7 @@ int run_umma(const float* act, const long long* as, int IH, int IW, const float*
   }
   {
     const int taps = p.KH * p.KW;
-    const int BN = p.Cout > 256 ? 256 : p.Cout;
+    const int BN = (p.Cout == 256 && cfg != 1 && cfg != 5) ? 128 : (p.Cout > 256 ? 256 : p.Cout);
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
     cuuint32_t box[3] = {KCH, (cuuint32_t)BN, 1};
@@ -293,7 +300,15 @@ int run_umma(const float* act, const long long* as, int IH, int IW, const float*
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
   }
-  if (p.Cout == 256) return launch_umma<256, 2, 3, 1>(tmA, tmB, bias, y, p, st, who);
+  if (p.Cout == 256) {
+    // two 128-channel halves per pixel group: 48 KB stages x 4 and double-buffered accumulators beat one
+    // 256-wide tile (64 KB x 3, no epilogue overlap): 552 vs 430 TFLOP/s on the ResnetBlock conv at batch 32
+    if (cfg == 1) return launch_umma<256, 1, 4, 2>(tmA, tmB, bias, y, p, st, who);
+    if (cfg == 5) return launch_umma<256, 2, 3, 1>(tmA, tmB, bias, y, p, st, who);
+    if (cfg == 3) return launch_umma<128, 4, 2, 1>(tmA, tmB, bias, y, p, st, who);
+    if (cfg == 4) return launch_umma<128, 1, 6, 2>(tmA, tmB, bias, y, p, st, who);
+    return launch_umma<128, 2, 4, 2>(tmA, tmB, bias, y, p, st, who);
+  }
   if (p.Cout == 128) return launch_umma<128, 2, 4, 2>(tmA, tmB, bias, y, p, st, who);
   return launch_umma<64, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
 }

@@ -185,25 +185,45 @@ in_stats_v4_kernel(const float4* __restrict__ x, double* __restrict__ sums, int 
   }
 }
 
-// grid (ceil(WP*C4/256), HP, N)
+// grid (chunks, N); thread = (channel quad c4, pixel lane): the (mean, rstd) of its four channels are
+// loaded once, then it walks the padded pixels of its chunk four at a time (four loads in flight).
 __global__ void __launch_bounds__(256)
 in_apply_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ stats, const float4* __restrict__ res,
-                   float4* __restrict__ y, int H, int W, int C4, int relu, int p, int rp) {
-  const int HP = H + 2 * p, WP = W + 2 * p;
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e >= WP * C4) return;
-  const int wp = e / C4, c4 = e - wp * C4;
-  const int hp = blockIdx.y, n = blockIdx.z;
-  const int h = reflect_idx(hp - p, H), w = reflect_idx(wp - p, W);
+                   float4* __restrict__ y, int H, int W, int C4, int relu, int p, int rp, int chunk) {
+  const int HP = H + 2 * p, WP = W + 2 * p, RW = W + 2 * rp;
+  const int total = HP * WP;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * chunk, p1 = min(total, p0 + chunk);
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, npl = 256 / C4;
+  if (pl >= npl) return;
   const float4 s0 = __ldg(stats + ((long long)n * C4 + c4) * 2), s1 = __ldg(stats + ((long long)n * C4 + c4) * 2 + 1);
-  float4 v = x[(((long long)n * H + h) * W + w) * C4 + c4];
-  v.x = (v.x - s0.x) * s0.y; v.y = (v.y - s0.z) * s0.w; v.z = (v.z - s1.x) * s1.y; v.w = (v.w - s1.z) * s1.w;
-  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-  if (res) {
-    const float4 r = res[(((long long)n * (H + 2 * rp) + h + rp) * (W + 2 * rp) + w + rp) * C4 + c4];
-    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  const float4* xb = x + (long long)n * H * W * C4 + c4;
+  const float4* rb = res ? res + (long long)n * (H + 2 * rp) * RW * C4 + c4 : nullptr;
+  float4* yb = y + (long long)n * total * C4 + c4;
+  for (int pp = p0 + pl; pp < p1; pp += 4 * npl) {
+    float4 v[4], r[4];
+    int ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int q = pp + k * npl;
+      ok[k] = q < p1;
+      if (ok[k]) {
+        const int hp = q / WP, wp = q - hp * WP;
+        const int h = reflect_idx(hp - p, H), w = reflect_idx(wp - p, W);
+        v[k] = xb[((long long)h * W + w) * C4];
+        if (rb) r[k] = rb[((long long)(h + rp) * RW + w + rp) * C4];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      float4 t = v[k];
+      t.x = (t.x - s0.x) * s0.y; t.y = (t.y - s0.z) * s0.w; t.z = (t.z - s1.x) * s1.y; t.w = (t.w - s1.z) * s1.w;
+      if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+      if (rb) { t.x += r[k].x; t.y += r[k].y; t.z += r[k].z; t.w += r[k].w; }
+      yb[(long long)(pp + k * npl) * C4] = t;
+    }
   }
-  y[(((long long)n * HP + hp) * WP + wp) * C4 + c4] = v;
 }
 
 __global__ void __launch_bounds__(256)
@@ -257,29 +277,54 @@ in_bwd_reduce_v4_kernel(const float4* __restrict__ dy, const float4* __restrict_
   }
 }
 
-// grid (ceil(HW*C4/256), N)
+// grid (chunks, N); thread = (channel quad, pixel lane), statistics hoisted out of the pixel loop
 __global__ void __launch_bounds__(256)
 in_bwd_apply_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ stats, const double* __restrict__ sums,
-                       float4* __restrict__ dx, int HW, int C4) {
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= (long long)HW * C4) return;
+                       float4* __restrict__ dx, int HW, int C4, int chunk) {
   const int n = blockIdx.y;
-  const int c4 = (int)(e % C4);
-  const long long i = (long long)n * HW * C4 + e;
+  const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+  const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, npl = 256 / C4;
+  if (pl >= npl) return;
   const float4 s0 = __ldg(stats + ((long long)n * C4 + c4) * 2), s1 = __ldg(stats + ((long long)n * C4 + c4) * 2 + 1);
   const double* sm = sums + ((long long)n * C4 * 4 + c4 * 4) * 2;
   const double inv = 1.0 / HW;
   const float mean[4] = {s0.x, s0.z, s1.x, s1.z}, rstd[4] = {s0.y, s0.w, s1.y, s1.w};
-  const float4 xv = x[i], gv = dx[i];
-  const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
-  float r[4];
+  float m1[4], m2[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float m1 = (float)(sm[2 * j] * inv), m2 = (float)(sm[2 * j + 1] * inv);
-    const float xh = (xs[j] - mean[j]) * rstd[j];
-    r[j] = rstd[j] * (gs[j] - m1 - xh * m2);
+  for (int j = 0; j < 4; ++j) { m1[j] = (float)(sm[2 * j] * inv); m2[j] = (float)(sm[2 * j + 1] * inv); }
+  const float4* xb = x + (long long)n * HW * C4 + c4;
+  float4* gb = dx + (long long)n * HW * C4 + c4;
+  for (int pp = p0 + pl; pp < p1; pp += 4 * npl) {
+    float4 xv[4], gv[4];
+    int ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int q = pp + k * npl;
+      ok[k] = q < p1;
+      if (ok[k]) { xv[k] = xb[(long long)q * C4]; gv[k] = gb[(long long)q * C4]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const float xs[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w}, gs[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xs[j] - mean[j]) * rstd[j];
+        r[j] = rstd[j] * (gs[j] - m1[j] - xh * m2[j]);
+      }
+      gb[(long long)(pp + k * npl) * C4] = make_float4(r[0], r[1], r[2], r[3]);
+    }
   }
-  dx[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// chunk of pixels per CTA for the elementwise instance-norm passes: ~16 CTAs per SM
+static int apply_chunk(int pixels, int N, int* nchunks) {
+  int want = (16 * dfmir_num_sms() + N - 1) / N;
+  int chunk = (pixels + want - 1) / want;
+  if (chunk < 64) chunk = 64;
+  *nchunks = (pixels + chunk - 1) / chunk;
+  return chunk;
 }
 
 static inline bool in_v4_ok(int C, const void* a, const void* b, const void* c, const void* d) {
@@ -527,10 +572,10 @@ upcat_bwd_kernel(const float* __restrict__ dy, float* __restrict__ da, float* __
 extern "C" size_t dfmir_instnorm_workspace_bytes(int N, int C) { return sizeof(double) * 2 * (size_t)N * C + 256; }
 
 static int in_chunk(int HW, int N, int* nchunks) {
-  // enough CTAs for ~4 per SM, at least 256 pixels per CTA
-  int want = (4 * dfmir_num_sms() + N - 1) / N;
+  // enough CTAs for ~8 per SM (full occupancy at 256 threads), at least 128 pixels per CTA
+  int want = (8 * dfmir_num_sms() + N - 1) / N;
   int chunk = (HW + want - 1) / want;
-  if (chunk < 256) chunk = 256;
+  if (chunk < 128) chunk = 128;
   *nchunks = (HW + chunk - 1) / chunk;
   return chunk;
 }
@@ -553,9 +598,9 @@ extern "C" int dfmir_instnorm_fwd(const float* x, const float* res, float* y, fl
   in_finalize_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, stats, N * C, H * W, eps);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(finalize)");
   if (v4) {
-    const int HP = H + 2 * out_pad, WP = W + 2 * out_pad;
-    in_apply_v4_kernel<<<dim3((WP * (C / 4) + 255) / 256, HP, N), 256, 0, st>>>(
-        (const float4*)x, (const float4*)stats, (const float4*)res, (float4*)y, H, W, C / 4, relu, out_pad, res_pad);
+    int ach; const int achunk = apply_chunk((H + 2 * out_pad) * (W + 2 * out_pad), N, &ach);
+    in_apply_v4_kernel<<<dim3(ach, N), 256, 0, st>>>((const float4*)x, (const float4*)stats, (const float4*)res, (float4*)y, H, W,
+                                                     C / 4, relu, out_pad, res_pad, achunk);
   } else {
     const long long total = (long long)N * (H + 2 * out_pad) * (W + 2 * out_pad) * C;
     in_apply_kernel<<<ew_grid(total), 256, 0, st>>>(x, stats, res, y, N, H, W, C, relu, out_pad, res_pad);
@@ -581,8 +626,8 @@ extern "C" int dfmir_instnorm_bwd(const float* dy, const float* x, const float* 
     in_bwd_reduce_v4_kernel<<<dim3(nch, N), 256, 0, st>>>((const float4*)dy, (const float4*)x, (const float4*)stats, (float4*)dx,
                                                           (float4*)dres, sums, H, W, C / 4, relu, out_pad, res_pad, chunk);
     DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(reduce)");
-    in_bwd_apply_v4_kernel<<<dim3((unsigned)(((long long)H * W * (C / 4) + 255) / 256), N), 256, 0, st>>>(
-        (const float4*)x, (const float4*)stats, sums, (float4*)dx, H * W, C / 4);
+    int ach; const int achunk = apply_chunk(H * W, N, &ach);
+    in_bwd_apply_v4_kernel<<<dim3(ach, N), 256, 0, st>>>((const float4*)x, (const float4*)stats, sums, (float4*)dx, H * W, C / 4, achunk);
     DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(apply)");
     return DFMIR_OK;
   }
