@@ -20,35 +20,46 @@ CONV_ENGINE = os.environ.get("DFMIR_CONV_ENGINE", "auto")
 
 
 class ConvProfile:
-    """bench.py instrumentation: CUDA-event pairs around every convolution launch on the launching
-    stream, with the algorithmic FLOPs (2*M*N*K) of each call."""
+    """bench.py instrumentation: a CUDA-event pair around every convolution kernel launch (the C-ABI
+    call only, on the launching stream), keyed by kernel kind, with the algorithmic FLOPs (2*M*N*K)
+    of each call.  Kinds: umma_fwd / umma_dgrad / umma_wgrad (tcgen05 engine), simt (fp32 engine,
+    including the direct 7x7 stem / head kernels)."""
 
     def __init__(self):
-        self.events, self.flops, self.calls, self.umma_calls = [], 0.0, 0, 0
+        self.events = []          # (kind, start, end, flops)
+        self.calls, self.umma_calls = 0, 0
 
-    def run(self, fn, flops, umma=False):
+    def run(self, fn, flops, kind):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
         e.record()
-        self.events.append((s, e))
-        self.flops += flops
+        self.events.append((kind, s, e, flops))
         self.calls += 1
-        self.umma_calls += int(umma)
+        self.umma_calls += int(kind.startswith("umma"))
+
+    def by_kind(self):
+        """{kind: (total ms, total flops, calls)}"""
+        torch.cuda.synchronize()
+        out = {}
+        for kind, s, e, fl in self.events:
+            ms, f, n = out.get(kind, (0.0, 0.0, 0))
+            out[kind] = (ms + s.elapsed_time(e), f + fl, n + 1)
+        return out
 
     def total(self):
-        torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in self.events), self.flops, self.calls
+        k = self.by_kind()
+        return sum(v[0] for v in k.values()), sum(v[1] for v in k.values()), self.calls
 
 
 PROFILE = None
 
 
-def _run(fn, flops, umma=False):
+def _run(fn, flops, kind="simt"):
     if PROFILE is None:
         fn()
     else:
-        PROFILE.run(fn, flops, umma)
+        PROFILE.run(fn, flops, kind)
 
 
 class ConvDesc(ctypes.Structure):
@@ -126,7 +137,7 @@ class _ConvFn(torch.autograd.Function):
         flops = 2.0 * N * math.prod(O) * Cout * w.shape[0] * Cin
         if _use_umma((nd, Cin, Cout, kernel, stride, pad, x, planar_out)):
             from . import umma
-            _run(lambda: umma.conv_fwd(x, w, bias, y, d), flops, True)
+            umma.conv_fwd(x, w, bias, y, d, flops)
             engine = "umma"
         else:
             _run(lambda: _lib.call("dfmir_conv_fwd", x, w, bias, y, ctypes.byref(d)), flops)
@@ -153,7 +164,7 @@ class _ConvFn(torch.autograd.Function):
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
             if engine == "umma":
                 from . import umma
-                _run(lambda: umma.conv_dgrad(dy, w, dx, d), flops, True)
+                umma.conv_dgrad(dy, w, dx, d, flops)
             else:
                 wt = w.transpose(1, 2).contiguous()
                 _run(lambda: _lib.call("dfmir_conv_dgrad", dy, wt, dx, ctypes.byref(d)), flops)
@@ -163,7 +174,7 @@ class _ConvFn(torch.autograd.Function):
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(x, nd), ys)
             if engine == "umma":
                 from . import umma
-                _run(lambda: umma.conv_wgrad(x, dy, dw, db, d), flops, True)
+                umma.conv_wgrad(x, dy, dw, db, d, flops)
             else:
                 _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops)
         return dx, dw, db, None, None, None, None, None

@@ -70,6 +70,17 @@ def open_image_to_torch(path, size):
     return _test_image_cache[key]
 
 
+def global_mask_scale(msum, world):
+    """Factor that turns a rank-local masked mean  S_r / M_r  into this rank's share of the global-batch
+    masked mean  sum_r S_r / sum_r M_r  (reference registration_model.py:262-263 divides by the mask sum of
+    the WHOLE batch): after gradients are averaged over the `world` ranks,
+    mean_r[(S_r / M_r) * (M_r * world / sum M)] = sum S / sum M.  One scalar all-reduce."""
+    import torch.distributed as dist
+    total = msum.clone()
+    dist.all_reduce(total)
+    return torch.where(total > 0, msum * world / total.clamp_min(1e-20), torch.ones_like(total))
+
+
 def smooothing_loss(y_pred):
     return losses.smooothing_loss(y_pred)
 
@@ -266,12 +277,7 @@ class REGISTRATIONModel(BaseModel):
     def _masked_l1(self, src, tgt, mu, mv):
         loss, msum = losses.l1_threshold_masked(src, tgt, mu, mv, thr=-0.95, return_mask_sum=True)
         if self._world > 1:
-            # exact global-batch normalisation: sum over ranks of |d|*m / sum over ranks of m
-            import torch.distributed as dist
-            total = msum.detach().clone()
-            dist.all_reduce(total)
-            scale = torch.where(total > 0, msum.detach() * self._world / total.clamp_min(1e-20), torch.ones_like(total))
-            loss = loss * scale
+            loss = loss * global_mask_scale(msum.detach(), self._world)
         return loss
 
     def set_input(self, input):

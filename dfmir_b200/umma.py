@@ -16,17 +16,23 @@ def supported(nd, Cin, Cout, kernel, stride, pad, x, planar_out):
     return st[3] == 1 and all(s % 4 == 0 for s in st[:3]) and x.data_ptr() % 16 == 0
 
 
-def conv_fwd(x, w, bias, y, d):
+def _run(fn, flops, kind):
+    from . import functional as Fn
+    Fn._run(fn, flops, kind)
+
+
+def conv_fwd(x, w, bias, y, d, flops=0.0):
     wk = w.transpose(1, 2).contiguous()          # [tap][Cout][Cin]: K-major rows for the B operand
-    _lib.call("dfmir_conv_umma_fwd", x, wk, bias, y, ctypes.byref(d))
+    _run(lambda: _lib.call("dfmir_conv_umma_fwd", x, wk, bias, y, ctypes.byref(d)), flops, "umma_fwd")
 
 
-def conv_dgrad(dy, w, dx, d):
-    _lib.call("dfmir_conv_umma_dgrad", dy, w, dx, ctypes.byref(d))   # [tap][Cin][Cout] is K-major here
+def conv_dgrad(dy, w, dx, d, flops=0.0):
+    # [tap][Cin][Cout] is K-major for this product
+    _run(lambda: _lib.call("dfmir_conv_umma_dgrad", dy, w, dx, ctypes.byref(d)), flops, "umma_dgrad")
 
 
-def conv_wgrad(x, dy, dw, db, d):
+def conv_wgrad(x, dy, dw, db, d, flops=0.0):
     if _lib.lib().dfmir_conv_umma_wgrad_supported(ctypes.byref(d)):
-        _lib.call("dfmir_conv_umma_wgrad", x, dy, dw, db, ctypes.byref(d))
+        _run(lambda: _lib.call("dfmir_conv_umma_wgrad", x, dy, dw, db, ctypes.byref(d)), flops, "umma_wgrad")
     else:
-        _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d))
+        _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops, "simt")

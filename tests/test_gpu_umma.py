@@ -64,8 +64,8 @@ def test_umma_conv_fwd_dgrad(case):
         tc, prof = run("auto")
     finally:
         Fn.CONV_ENGINE, Fn.PROFILE = "auto", None
-    assert prof.umma_calls == 3, "forward, dgrad and wgrad must all run on the tensor-core engine"
     wgrad_tc = bool(_wgrad_supported(Cin, Cout))
+    assert prof.umma_calls == (3 if wgrad_tc else 2), "forward, dgrad (and wgrad where covered) must run on the tensor-core engine"
     for name, got, want, ex, em in (("fwd", tc[0], y.detach(), exact[0], emu[0]), ("dgrad", tc[1], x.grad, exact[1], emu[1]),
                                     ("wgrad", tc[2], w.grad, exact[2], emu[2])):
         scale = float(want.abs().max())
