@@ -162,11 +162,16 @@ in_stats_v4_kernel(const float4* __restrict__ x, double* __restrict__ sums, int 
     int px = p0 + pl;
     while (px < p1) {
       float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int k = 0; k < 16 && px < p1; ++k, px += npl) {
-        const float4 v = xb[(long long)px * C4];
-        fs[0] += v.x; fs[1] += v.y; fs[2] += v.z; fs[3] += v.w;
-        fq[0] = fmaf(v.x, v.x, fq[0]); fq[1] = fmaf(v.y, v.y, fq[1]); fq[2] = fmaf(v.z, v.z, fq[2]); fq[3] = fmaf(v.w, v.w, fq[3]);
+      for (int k = 0; k < 4 && px < p1; ++k, px += 4 * npl) {      // 4 x 4 pixels in fp32, then into fp64
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (px + u * npl < p1) ? xb[(long long)(px + u * npl) * C4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          fs[0] += v[u].x; fs[1] += v[u].y; fs[2] += v[u].z; fs[3] += v[u].w;
+          fq[0] = fmaf(v[u].x, v[u].x, fq[0]); fq[1] = fmaf(v[u].y, v[u].y, fq[1]);
+          fq[2] = fmaf(v[u].z, v[u].z, fq[2]); fq[3] = fmaf(v[u].w, v[u].w, fq[3]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) { s[j] += (double)fs[j]; ss[j] += (double)fq[j]; }
@@ -239,30 +244,55 @@ in_bwd_reduce_v4_kernel(const float4* __restrict__ dy, const float4* __restrict_
   double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (pl < npl) {
     const float4 s0 = __ldg(stats + ((long long)n * C4 + c4) * 2), s1 = __ldg(stats + ((long long)n * C4 + c4) * 2 + 1);
-    int px = p0 + pl;
-    while (px < p1) {
-      float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = 0; k < 16 && px < p1; ++k, px += npl) {
-        const int h = px / W, w = px - h * W;
-        int hl[3], wl[3];
-        const int nh = fold_list(h, H, p, hl), nw = fold_list(w, W, p, wl);
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int a = 0; a < nh; ++a)
-          for (int b = 0; b < nw; ++b) acc4(g, dy[(((long long)n * HP + hl[a]) * WP + wl[b]) * C4 + c4]);
-        const long long o = ((long long)n * HW + px) * C4 + c4;
+    const float4* dyb = dy + (long long)n * HP * WP * C4 + c4;
+    const float4* xb = x + (long long)n * HW * C4 + c4;
+    float4* dxb = dx + (long long)n * HW * C4 + c4;
+    float f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+    int flush = 0;
+    for (int px = p0 + pl; px < p1; px += 4 * npl) {
+      // four pixels per trip: the centre gradient and x loads of all four are issued before any is used
+      float4 gv[4], xv[4];
+      int hh[4], ww[4], ok[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = px + k * npl;
+        ok[k] = q < p1;
+        hh[k] = ok[k] ? q / W : 0; ww[k] = ok[k] ? q - hh[k] * W : 0;
+        if (ok[k]) {
+          gv[k] = dyb[((long long)(hh[k] + p) * WP + ww[k] + p) * C4];
+          xv[k] = xb[(long long)q * C4];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        const int h = hh[k], w = ww[k];
+        float g[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+        if (p > 0 && (h <= p || w <= p || h >= H - 1 - p || w >= W - 1 - p)) {
+          // halo pixels of the reflected padding alias this interior pixel: add their gradients
+          int hl[3], wl[3];
+          const int nh = fold_list(h, H, p, hl), nw = fold_list(w, W, p, wl);
+          for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b)
+              if (a | b) acc4(g, dyb[((long long)hl[a] * WP + wl[b]) * C4]);
+        }
         if (dres) dres[(((long long)n * (H + 2 * rp) + h + rp) * (W + 2 * rp) + w + rp) * C4 + c4] = make_float4(g[0], g[1], g[2], g[3]);
-        const float4 xv = x[o];
-        const float xh[4] = {(xv.x - s0.x) * s0.y, (xv.y - s0.z) * s0.w, (xv.z - s1.x) * s1.y, (xv.w - s1.z) * s1.w};
+        const float xh[4] = {(xv[k].x - s0.x) * s0.y, (xv[k].y - s0.z) * s0.w, (xv[k].z - s1.x) * s1.y, (xv[k].w - s1.z) * s1.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (relu && !(xh[j] > 0.f)) g[j] = 0.f;
           f1[j] += g[j]; f2[j] = fmaf(g[j], xh[j], f2[j]);
         }
-        dx[o] = make_float4(g[0], g[1], g[2], g[3]);
+        dxb[(long long)(px + k * npl) * C4] = make_float4(g[0], g[1], g[2], g[3]);
       }
+      if (++flush == 4) {      // fp32 partial sums over at most 16 pixels, then into fp64
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { s[2 * j] += (double)f1[j]; s[2 * j + 1] += (double)f2[j]; }
+        for (int j = 0; j < 4; ++j) { s[2 * j] += (double)f1[j]; s[2 * j + 1] += (double)f2[j]; f1[j] = 0.f; f2[j] = 0.f; }
+        flush = 0;
+      }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[2 * j] += (double)f1[j]; s[2 * j + 1] += (double)f2[j]; }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];

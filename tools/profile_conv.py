@@ -22,7 +22,7 @@ for it in range(reps):
     y.backward(gy)
     Fn.PROFILE = None
     torch.cuda.synchronize()
-    ts = [s.elapsed_time(e) for s, e in prof.events]
+    ts = [s.elapsed_time(e) for _, s, e, _ in prof.events]
     print("rep %d: fwd %.3f ms (%.0f TF/s)  dgrad %.3f ms (%.0f TF/s)  wgrad+bias %.3f ms (%.0f TF/s)" % (
         it, ts[0], flops / ts[0] / 1e9, ts[1], flops / ts[1] / 1e9, ts[2], flops / ts[2] / 1e9))
     x.grad = None; w.grad = None; b.grad = None
