@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DFMIR_ABI_VERSION 2
+#define DFMIR_ABI_VERSION 3
 
 #define DFMIR_INTERP_LINEAR 0
 #define DFMIR_INTERP_NEAREST 1
@@ -59,6 +59,18 @@ int dfmir_vecint_fwd(const float* vel, float* steps, int B, int nd, const int* s
 /* work: 2 slabs (Bv,nd,*S) scratch; d_vel (B,nd,*S) overwritten. */
 int dfmir_vecint_bwd(const float* grad_out, const float* vel, const float* steps, float* work, float* d_vel,
                      int B, int nd, const int* shape, int nsteps, int bidir, int coord_mode, void* stream);
+
+/* ---- K4+K5 fused: ONE cooperative launch for integrate -> resize x2 -> warp -> NCC + Grad
+ * (vxm networks.py:1129-1139 tail of VxmDense.forward + util/losses.py:92-130, 183-261).
+ * vel (B,nd,*half) -> steps (nsteps,B,nd,*half) every squaring step (kept for the backward), flow_full
+ * (B,nd,*2half), warped (B,C,*2half), out[4] = {ncc loss, sum cc, voxel count, grad loss}.
+ * ncc_reduction / grad_penalty / grad_mult as in dfmir_ncc_fwd / dfmir_grad_loss_fwd; win in {5,7,9}.
+ * flow_full and warped are bit-identical to dfmir_vecint_fwd + dfmir_resize_linear_fwd + dfmir_warp_fwd. */
+size_t dfmir_fused_reg_workspace_bytes(void);
+int dfmir_fused_reg_fwd(const float* vel, const float* moving, const float* fixed, float* steps, float* flow_full,
+                        float* warped, float* out, void* ws, size_t ws_bytes, int B, int C, int nd,
+                        const int* half_shape, int nsteps, int win, float eps, int ncc_reduction, int grad_penalty,
+                        float grad_mult, int coord_mode, void* stream);
 
 /* ---- ResizeTransform.forward — layers.py:85-97 (F.interpolate align_corners=True + rescale)
  * y = post_mul * interp(pre_mul * x); x (BC,*in_shape) -> y (BC,*out_shape). */
