@@ -43,10 +43,11 @@ struct FusedP {
   int G3[3];                // full-resolution dims right-aligned for the Grad loss (2-D: {1,H,W})
 };
 
+// element loops run on 32-bit indices (the host entry rejects volumes with B * nd * nvox >= 2^31)
 template <int ND>
-__device__ __forceinline__ void unravel(long long v, const int* S, int* pos) {
+__device__ __forceinline__ void unravel(int v, const int* S, int* pos) {
 #pragma unroll
-  for (int d = ND - 1; d >= 0; --d) { pos[d] = (int)(v % S[d]); v /= S[d]; }
+  for (int d = ND - 1; d >= 0; --d) { pos[d] = v % S[d]; v /= S[d]; }
 }
 
 template <int ND, int WIN, int CM>
@@ -57,8 +58,9 @@ fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving
   extern __shared__ float smem[];
   __shared__ double sred[5][NT / 32];
   cg::grid_group grid = cg::this_grid();
-  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long gthreads = (long long)gridDim.x * blockDim.x;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gthreads = gridDim.x * blockDim.x;
+  const int nh = (int)p.nh, nf = (int)p.nf;
 
   // ---- phases 1..nsteps: scaling and squaring (same arithmetic as vecint_step_kernel)
   const long long slab = (long long)p.B * ND * p.nh;
@@ -67,9 +69,9 @@ fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving
     const float* in = k == 0 ? vel : steps + (long long)(k - 1) * slab;
     float* o = steps + (long long)k * slab;
     const float sc = k == 0 ? sc0 : 1.f;
-    for (long long it = gtid; it < (long long)p.B * p.nh; it += gthreads) {
-      const int b = (int)(it / p.nh);
-      const long long v = it - (long long)b * p.nh;
+    for (int it = gtid; it < p.B * nh; it += gthreads) {
+      const int b = it / nh;
+      const int v = it - b * nh;
       const float* ib = in + (long long)b * ND * p.nh;
       int pos[ND]; float f[ND];
       unravel<ND>(v, p.Sh, pos);
@@ -89,14 +91,14 @@ fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving
   // ---- phase nsteps+1: upsample the integrated field and warp the moving image
   {
     const float* field = steps + (long long)(p.nsteps - 1) * slab;
-    for (long long it = gtid; it < (long long)p.B * p.nf; it += gthreads) {
-      const int b = (int)(it / p.nf);
-      const long long v = it - (long long)b * p.nf;
+    for (int it = gtid; it < p.B * nf; it += gthreads) {
+      const int b = it / nf;
+      const int v = it - b * nf;
       int pos[ND]; float f[ND];
       unravel<ND>(v, p.Sf, pos);
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
-        f[d] = resizedev::interp<ND>(field + ((long long)b * ND + d) * p.nh, p.rg, v, p.pre_mul);   // post_mul = 1
+        f[d] = resizedev::interp<ND, int>(field + ((long long)b * ND + d) * p.nh, p.rg, v, p.pre_mul);   // post_mul = 1
         flow_full[((long long)b * ND + d) * p.nf + v] = f[d];
       }
       SampleSite<ND> s;
@@ -119,13 +121,13 @@ fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving
   }
   float acc[3] = {0.f, 0.f, 0.f};
   {
-    const long long st1 = p.G3[2], st0 = (long long)p.G3[1] * p.G3[2];
-    const long long total = (long long)p.B * ND * p.nf;
-    for (long long it = gtid; it < total; it += gthreads) {
-      const long long v = it % p.nf;
-      const int px = (int)(v % p.G3[2]);
-      const int py = (int)((v / p.G3[2]) % p.G3[1]);
-      const int pz = (int)(v / st0);
+    const int st1 = p.G3[2], st0 = p.G3[1] * p.G3[2];
+    const int total = p.B * ND * nf;
+    for (int it = gtid; it < total; it += gthreads) {
+      const int v = it % nf;
+      const int px = v % p.G3[2];
+      const int py = (v / p.G3[2]) % p.G3[1];
+      const int pz = v / st0;
       const float c = flow_full[it];
       if (px + 1 < p.G3[2]) { float d = fabsf(flow_full[it + 1] - c); acc[2] += p.grad_penalty == 2 ? d * d : d; }
       if (py + 1 < p.G3[1]) { float d = fabsf(flow_full[it + st1] - c); acc[1] += p.grad_penalty == 2 ? d * d : d; }
@@ -231,6 +233,8 @@ extern "C" int dfmir_fused_reg_fwd(const float* vel, const float* moving, const 
     if (d < nd) full_shape[d] = p.Sf[d];
     p.nh *= p.Sh[d]; p.nf *= p.Sf[d];
   }
+  DFMIR_CHECK_ARG((long long)B * nd * p.nf < (1LL << 31) && (long long)B * C * p.nf < (1LL << 31),
+                  "%s: volume too large for the 32-bit element loops (B * nd * voxels must stay below 2^31)", who);
   p.rg.BC = B * nd; p.rg.nin = p.nh; p.rg.nout = p.nf;
   for (int d = 0; d < 3; ++d) {
     p.rg.I[d] = p.Sh[d]; p.rg.O[d] = p.Sf[d];

@@ -200,15 +200,17 @@ namespace {
 
 struct GGeom { int P; int S[3]; int nd; long long nvox; };  // P = B*C planes
 
+// I: int when P * nvox < 2^31 (64-bit div/mod per element dominated this memory-bound kernel), else long long
+template <typename I>
 __global__ void __launch_bounds__(256)
 grad_fwd_kernel(const float* __restrict__ x, double* __restrict__ partials, GGeom g, int penalty) {
   __shared__ double sred[3][8];
   float acc[3] = {0.f, 0.f, 0.f};
-  const long long total = (long long)g.P * g.nvox;
-  const long long st1 = g.S[2], st0 = (long long)g.S[1] * g.S[2];
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const long long v = it % g.nvox;
+  const I nvox = (I)g.nvox;
+  const I total = (I)g.P * nvox;
+  const I st1 = g.S[2], st0 = (I)g.S[1] * g.S[2];
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
+    const I v = it % nvox;
     const int px = (int)(v % g.S[2]);
     const int py = (int)((v / g.S[2]) % g.S[1]);
     const int pz = (int)(v / st0);
@@ -235,36 +237,38 @@ grad_fwd_kernel(const float* __restrict__ x, double* __restrict__ partials, GGeo
 // means are added in the reference's order and divided by nd (util/losses.py:105-116).
 __global__ void grad_finalize_kernel(const double* __restrict__ partials, int n, float* __restrict__ loss,
                                      GGeom g, float loss_mult) {
+  // launched with 96 threads: warp k sums the partials of axis k
   __shared__ double s[3];
-  if (threadIdx.x < 3) {
-    double a = 0;
-    for (int i = 0; i < n; ++i) a += partials[3 * (long long)i + threadIdx.x];
-    s[threadIdx.x] = a;
-  }
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double a = 0;
+  for (int i = lane; i < n; i += 32) a += partials[3 * (long long)i + k];
+  a = warp_sum_d(a);
+  if (lane == 0) s[k] = a;
   __syncthreads();
   if (threadIdx.x == 0) {
     float d = 0.f;
-    for (int k = 2; k >= 3 - g.nd; --k) {  // x, y, (z): mean(dx) + mean(dy) + mean(dz)
-      const double cnt = (double)g.P * (double)(g.nvox / g.S[k]) * (double)(g.S[k] - 1);
-      d += (float)(s[k] / cnt);
+    for (int k2 = 2; k2 >= 3 - g.nd; --k2) {  // x, y, (z): mean(dx) + mean(dy) + mean(dz)
+      const double cnt = (double)g.P * (double)(g.nvox / g.S[k2]) * (double)(g.S[k2] - 1);
+      d += (float)(s[k2] / cnt);
     }
     loss[0] = d / (float)g.nd * loss_mult;
   }
 }
 
+template <typename I>
 __global__ void __launch_bounds__(256)
 grad_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grad_loss, float* __restrict__ dx,
                 GGeom g, int penalty, float loss_mult) {
-  const long long total = (long long)g.P * g.nvox;
-  const long long strd[3] = {(long long)g.S[1] * g.S[2], (long long)g.S[2], 1};
+  const I nvox = (I)g.nvox;
+  const I total = (I)g.P * nvox;
+  const I strd[3] = {(I)g.S[1] * g.S[2], (I)g.S[2], 1};
   float coef[3];
   for (int k = 0; k < 3; ++k) {
     const double cnt = (double)g.P * (double)(g.nvox / g.S[k]) * (double)(g.S[k] - 1);
     coef[k] = (k >= 3 - g.nd && cnt > 0) ? (float)((double)grad_loss[0] * loss_mult / ((double)g.nd * cnt)) : 0.f;
   }
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const long long v = it % g.nvox;
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
+    const I v = it % nvox;
     int p[3];
     p[2] = (int)(v % g.S[2]);
     p[1] = (int)((v / g.S[2]) % g.S[1]);
@@ -318,9 +322,10 @@ extern "C" int dfmir_grad_loss_fwd(const float* flow, float* loss, void* ws, siz
   const int grid = red_grid((long long)planes * g.nvox);
   DFMIR_CHECK_ARG(ws_bytes >= sizeof(double) * 3 * (size_t)grid, "dfmir_grad_loss_fwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  grad_fwd_kernel<<<grid, 256, 0, st>>>(flow, (double*)ws, g, penalty);
+  if ((long long)planes * g.nvox < (1LL << 31)) grad_fwd_kernel<int><<<grid, 256, 0, st>>>(flow, (double*)ws, g, penalty);
+  else grad_fwd_kernel<long long><<<grid, 256, 0, st>>>(flow, (double*)ws, g, penalty);
   DFMIR_CHECK_LAUNCH("dfmir_grad_loss_fwd");
-  grad_finalize_kernel<<<1, 32, 0, st>>>((const double*)ws, grid, loss, g, loss_mult);
+  grad_finalize_kernel<<<1, 96, 0, st>>>((const double*)ws, grid, loss, g, loss_mult);
   DFMIR_CHECK_LAUNCH("dfmir_grad_loss_fwd(finalize)");
   return DFMIR_OK;
 }
@@ -335,7 +340,8 @@ extern "C" int dfmir_grad_loss_bwd(const float* flow, const float* grad_loss, fl
   const long long items = (long long)planes * g.nvox;
   long long blocks = (items + 255) / 256;
   const long long cap = (long long)dfmir_num_sms() * 16;
-  grad_bwd_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(flow, grad_loss, d_flow, g, penalty, loss_mult);
+  if (items < (1LL << 31)) grad_bwd_kernel<int><<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(flow, grad_loss, d_flow, g, penalty, loss_mult);
+  else grad_bwd_kernel<long long><<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(flow, grad_loss, d_flow, g, penalty, loss_mult);
   DFMIR_CHECK_LAUNCH("dfmir_grad_loss_bwd");
   return DFMIR_OK;
 }

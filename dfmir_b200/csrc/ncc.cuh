@@ -33,20 +33,40 @@ __device__ __forceinline__ void box_march(const BoxGeom& g, Loader& ld, Consumer
   const int zo1 = min(g.D, zo0 + g.zchunk);
   const int rz = g.wz / 2;
 
+  // software pipeline: the halo tile of slice z+1 is fetched into registers while slice z is summed
+  constexpr int PER_T = (IY * IX + NT - 1) / NT;
+  float pre[PER_T][NQ];
+  auto prefetch = [&](int z) {
+    const bool zin = z >= 0 && z < g.D;
+#pragma unroll
+    for (int e = 0; e < PER_T; ++e) {
+      const int i = tid + e * NT;
+      if (zin && i < IY * IX) {
+        const int ly = i / IX, lx = i - ly * IX;
+        const int gy = y0 - R + ly, gx = x0 - R + lx;
+        const bool inb = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;
+        ld.load(b, z, gy, gx, inb, pre[e]);
+      }
+    }
+  };
+  prefetch(zo0 - rz);
   for (int z = zo0 - rz; z < zo1 + rz; ++z) {
     const bool zin = z >= 0 && z < g.D;
     const int slot = ((z % g.wz) + g.wz) % g.wz;
     if (zin) {
-      for (int i = tid; i < IY * IX; i += NT) {
-        const int ly = i / IX, lx = i - ly * IX;
-        const int gy = y0 - R + ly, gx = x0 - R + lx;
-        const bool inb = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;
-        float q[NQ];
-        ld.load(b, z, gy, gx, inb, q);
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) sIn[(k * IY + ly) * IX + lx] = q[k];
+      for (int e = 0; e < PER_T; ++e) {
+        const int i = tid + e * NT;
+        if (i < IY * IX) {
+          const int ly = i / IX, lx = i - ly * IX;
+#pragma unroll
+          for (int k = 0; k < NQ; ++k) sIn[(k * IY + ly) * IX + lx] = pre[e][k];
+        }
       }
-      __syncthreads();
+    }
+    __syncthreads();
+    if (z + 1 < zo1 + rz) prefetch(z + 1);
+    if (zin) {
       for (int i = tid; i < IY * TX; i += NT) {
         const int ly = i / TX, lx = i - ly * TX;
 #pragma unroll
@@ -75,16 +95,16 @@ __device__ __forceinline__ void box_march(const BoxGeom& g, Loader& ld, Consumer
     // sX are reused by the next slice.
     const int zo = z - rz;
     if (zo >= zo0 && zo < zo1) {
+      // sum the ring oldest slice first (z-rz .. z+rz ascending).  One modulo per slice, not per term:
+      // the slot of slice zo-rz, then +1 with wrap-around (90 integer divisions per voxel otherwise).
       float sums[NQ];
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) {
-        // sum the ring oldest slice first (z-rz .. z+rz ascending)
-        float s = 0.f;
-        for (int j = 0; j < g.wz; ++j) {
-          const int sl = (((zo - rz + j) % g.wz) + g.wz) % g.wz;
-          s += ring[(sl * NQ + k) * NT + tid];
-        }
-        sums[k] = s;
+      for (int k = 0; k < NQ; ++k) sums[k] = 0.f;
+      int sl = (((zo - rz) % g.wz) + g.wz) % g.wz;
+      for (int j = 0; j < g.wz; ++j) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) sums[k] += ring[(sl * NQ + k) * NT + tid];
+        if (++sl == g.wz) sl = 0;
       }
       const int oy = y0 + ty, ox = x0 + tx;
       if (oy < g.H && ox < g.W) cs.consume(b, zo, oy, ox, sums);

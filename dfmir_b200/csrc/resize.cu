@@ -10,30 +10,31 @@
 namespace {
 using namespace resizedev;
 
-template <int ND>
+// I: int when BC * nout < 2^31 (64-bit div/mod per element made this kernel integer-ALU bound), else long long
+template <int ND, typename I>
 __global__ void __launch_bounds__(256)
 resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, RGeom g, float pre_mul, float post_mul) {
-  const long long total = (long long)g.BC * g.nout;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(it / g.nout);
-    const long long v = it - (long long)p * g.nout;
-    const float r = interp<ND>(x + (long long)p * g.nin, g, v, pre_mul);
+  const I nout = (I)g.nout;
+  const I total = (I)g.BC * nout;
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
+    const int p = (int)(it / nout);
+    const I v = it - (I)p * nout;
+    const float r = interp<ND, I>(x + (long long)p * g.nin, g, v, pre_mul);
     y[it] = post_mul * r;
   }
 }
 
 // Adjoint: scatter gy * (pre_mul*post_mul) * weights into gx (pre-zeroed) with atomics.
-template <int ND>
+template <int ND, typename I>
 __global__ void __launch_bounds__(256)
 resize_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, RGeom g, float mul) {
-  const long long total = (long long)g.BC * g.nout;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(it / g.nout);
-    const long long v = it - (long long)p * g.nout;
+  const I nout = (I)g.nout;
+  const I total = (I)g.BC * nout;
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
+    const int p = (int)(it / nout);
+    const I v = it - (I)p * nout;
     int i0[ND], i1[ND]; float l0[ND], l1[ND];
-    setup<ND>(g, v, i0, i1, l0, l1);
+    setup<ND, I>(g, v, i0, i1, l0, l1);
     float* gp = gx + (long long)p * g.nin;
     const float go = gy[it] * mul;
 #pragma unroll
@@ -79,9 +80,15 @@ extern "C" int dfmir_resize_linear_fwd(const float* x, float* y, int BC, int nd,
   const long long items = (long long)BC * g.nout;
   if (items == 0) return DFMIR_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (nd == 1) resize_fwd_kernel<1><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
-  else if (nd == 2) resize_fwd_kernel<2><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
-  else resize_fwd_kernel<3><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
+  if (items < (1LL << 31)) {
+    if (nd == 1) resize_fwd_kernel<1, int><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
+    else if (nd == 2) resize_fwd_kernel<2, int><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
+    else resize_fwd_kernel<3, int><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
+  } else {
+    if (nd == 1) resize_fwd_kernel<1, long long><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
+    else if (nd == 2) resize_fwd_kernel<2, long long><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
+    else resize_fwd_kernel<3, long long><<<grid_for(items), 256, 0, st>>>(x, y, g, pre_mul, post_mul);
+  }
   DFMIR_CHECK_LAUNCH("dfmir_resize_linear_fwd");
   return DFMIR_OK;
 }
@@ -96,9 +103,15 @@ extern "C" int dfmir_resize_linear_bwd(const float* gy, float* gx, int BC, int n
   const long long items = (long long)BC * g.nout;
   if (items == 0) return DFMIR_OK;
   const float mul = pre_mul * post_mul;
-  if (nd == 1) resize_bwd_kernel<1><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
-  else if (nd == 2) resize_bwd_kernel<2><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
-  else resize_bwd_kernel<3><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
+  if (items < (1LL << 31)) {
+    if (nd == 1) resize_bwd_kernel<1, int><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
+    else if (nd == 2) resize_bwd_kernel<2, int><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
+    else resize_bwd_kernel<3, int><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
+  } else {
+    if (nd == 1) resize_bwd_kernel<1, long long><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
+    else if (nd == 2) resize_bwd_kernel<2, long long><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
+    else resize_bwd_kernel<3, long long><<<grid_for(items), 256, 0, st>>>(gy, gx, g, mul);
+  }
   DFMIR_CHECK_LAUNCH("dfmir_resize_linear_bwd");
   return DFMIR_OK;
 }

@@ -12,8 +12,8 @@ struct RGeom {
   long long nin, nout;
 };
 
-template <int ND>
-__device__ __forceinline__ void setup(const RGeom& g, long long v, int* i0, int* i1, float* l0, float* l1) {
+template <int ND, typename I>
+__device__ __forceinline__ void setup(const RGeom& g, I v, int* i0, int* i1, float* l0, float* l1) {
 #pragma unroll
   for (int d = ND - 1; d >= 0; --d) {
     const int o = (int)(v % g.O[d]);
@@ -30,10 +30,10 @@ __device__ __forceinline__ void setup(const RGeom& g, long long v, int* i0, int*
 
 
 // value of output voxel v of one plane: pre_mul is applied to every input sample (layers.py:91-94)
-template <int ND>
-__device__ __forceinline__ float interp(const float* __restrict__ xp, const RGeom& g, long long v, float pre_mul) {
+template <int ND, typename I>
+__device__ __forceinline__ float interp(const float* __restrict__ xp, const RGeom& g, I v, float pre_mul) {
   int i0[ND], i1[ND]; float l0[ND], l1[ND];
-  setup<ND>(g, v, i0, i1, l0, l1);
+  setup<ND, I>(g, v, i0, i1, l0, l1);
   float r;
   if (ND == 1) {
     r = l0[0] * (pre_mul * xp[i0[0]]) + l1[0] * (pre_mul * xp[i1[0]]);

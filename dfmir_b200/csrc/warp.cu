@@ -16,8 +16,8 @@ struct Geom {
   long long nvox;    // prod(S)
 };
 
-template <int ND>
-__device__ __forceinline__ void unravel(long long v, const int* S, int* pos) {
+template <int ND, typename I>
+__device__ __forceinline__ void unravel(I v, const int* S, int* pos) {
 #pragma unroll
   for (int d = ND - 1; d >= 0; --d) {
     pos[d] = (int)(v % S[d]);
@@ -27,18 +27,19 @@ __device__ __forceinline__ void unravel(long long v, const int* S, int* pos) {
 
 // ---------------------------------------------------------------- forward, linear / nearest
 // VEC consecutive x positions per thread; flow is read and out written as float4 when VEC == 4.
-template <int ND, int COORD_MODE, int VEC, bool NEAREST>
+// I: index type of the element loops — int when B * nvox < 2^31 (64-bit div/mod per voxel would dominate
+// these memory-bound kernels), long long otherwise.
+template <int ND, int COORD_MODE, int VEC, bool NEAREST, typename I>
 __global__ void __launch_bounds__(256)
 warp_fwd_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
                 int32_t* __restrict__ idx_out, Geom g) {
-  const long long items_per_b = g.nvox / VEC;
-  const long long total = (long long)g.B * items_per_b;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
+  const I items_per_b = (I)(g.nvox / VEC);
+  const I total = (I)g.B * items_per_b;
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
     const int b = (int)(it / items_per_b);
-    const long long v0 = (it - (long long)b * items_per_b) * VEC;
+    const I v0 = (it - (I)b * items_per_b) * VEC;
     int pos[ND];
-    unravel<ND>(v0, g.S, pos);
+    unravel<ND, I>(v0, g.S, pos);
 
     float f[ND][VEC];
     const float* fb = flow + (long long)b * ND * g.nvox + v0;
@@ -119,18 +120,18 @@ warp_fwd_kernel(const float* __restrict__ src, const float* __restrict__ flow, f
 // ---------------------------------------------------------------- backward (linear only)
 // d_src is accumulated with fp32 atomics (caller zero-fills); d_flow is written directly.
 // d(ix)/d(flow) = 1 analytically (normalise . unnormalise), so d_flow[d] = sum_c d(out_c)/d(ix_d) * g_c.
-template <int ND, int COORD_MODE>
+template <int ND, int COORD_MODE, typename I>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ src,
                 const float* __restrict__ flow, float* __restrict__ d_src, float* __restrict__ d_flow,
                 Geom g) {
-  const long long total = (long long)g.B * g.nvox;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(it / g.nvox);
-    const long long v = it - (long long)b * g.nvox;
+  const I nvox = (I)g.nvox;
+  const I total = (I)g.B * nvox;
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
+    const int b = (int)(it / nvox);
+    const I v = it - (I)b * nvox;
     int pos[ND]; float f[ND];
-    unravel<ND>(v, g.S, pos);
+    unravel<ND, I>(v, g.S, pos);
 #pragma unroll
     for (int d = 0; d < ND; ++d) f[d] = flow[((long long)b * ND + d) * g.nvox + v];
     SampleSite<ND> s;
@@ -188,20 +189,20 @@ warp_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ src,
 // negated flow of vxm/networks.py:1125 is integrated in the same launch as virtual batches
 // B..2B-1). Later steps: B_in = Bv, scales 1. Scaling by +-2^-n commutes exactly with fp32
 // rounding, so sampling the unscaled field and scaling is bit-identical to layers.py:65.
-template <int ND, int COORD_MODE>
+template <int ND, int COORD_MODE, typename I>
 __global__ void __launch_bounds__(256)
 vecint_step_kernel(const float* __restrict__ in, float* __restrict__ out, int B_in, int Bv,
                    float scale_lo, float scale_hi, Geom g) {
-  const long long total = (long long)Bv * g.nvox;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int bv = (int)(it / g.nvox);
-    const long long v = it - (long long)bv * g.nvox;
+  const I nvox = (I)g.nvox;
+  const I total = (I)Bv * nvox;
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
+    const int bv = (int)(it / nvox);
+    const I v = it - (I)bv * nvox;
     const int bi = bv % B_in;
     const float sc = bv < B_in ? scale_lo : scale_hi;
     const float* ib = in + (long long)bi * ND * g.nvox;
     int pos[ND]; float f[ND];
-    unravel<ND>(v, g.S, pos);
+    unravel<ND, I>(v, g.S, pos);
 #pragma unroll
     for (int d = 0; d < ND; ++d) f[d] = ib[(long long)d * g.nvox + v] * sc;
     SampleSite<ND> s;
@@ -216,22 +217,22 @@ vecint_step_kernel(const float* __restrict__ in, float* __restrict__ out, int B_
 
 // Backward of one step. g_in (pre-zeroed, shape (B_in, nd, S)) receives, via atomics,
 //   sc * [ g_out (identity term) + d_flow term ] at the voxel itself and sc * w * g_out at the corners.
-template <int ND, int COORD_MODE>
+template <int ND, int COORD_MODE, typename I>
 __global__ void __launch_bounds__(256)
 vecint_step_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ in,
                        float* __restrict__ g_in, int B_in, int Bv, float scale_lo, float scale_hi,
                        Geom g) {
-  const long long total = (long long)Bv * g.nvox;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int bv = (int)(it / g.nvox);
-    const long long v = it - (long long)bv * g.nvox;
+  const I nvox = (I)g.nvox;
+  const I total = (I)Bv * nvox;
+  for (I it = (I)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (I)gridDim.x * blockDim.x) {
+    const int bv = (int)(it / nvox);
+    const I v = it - (I)bv * nvox;
     const int bi = bv % B_in;
     const float sc = bv < B_in ? scale_lo : scale_hi;
     const float* ib = in + (long long)bi * ND * g.nvox;
     float* gb = g_in + (long long)bi * ND * g.nvox;
     int pos[ND]; float f[ND], go[ND], gf[ND];
-    unravel<ND>(v, g.S, pos);
+    unravel<ND, I>(v, g.S, pos);
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       f[d] = ib[(long long)d * g.nvox + v] * sc;
@@ -296,13 +297,18 @@ int launch_fwd(const float* src, const float* flow, float* out, int32_t* idx, co
   const long long items = (long long)g.B * g.nvox / (vec4 ? 4 : 1);
   if (items == 0) return DFMIR_OK;
   const int grid = grid_for(items, 256);
+  const bool narrow = (long long)g.B * g.nvox * (g.C > ND ? g.C : ND) < (1LL << 31);
+#define WARP_LAUNCH(V, NEAR)                                                                              \
+  do {                                                                                                    \
+    if (narrow) warp_fwd_kernel<ND, CM, V, NEAR, int><<<grid, 256, 0, st>>>(src, flow, out, idx, g);      \
+    else warp_fwd_kernel<ND, CM, V, NEAR, long long><<<grid, 256, 0, st>>>(src, flow, out, idx, g);       \
+  } while (0)
   if (interp == DFMIR_INTERP_NEAREST) {
-    if (vec4) warp_fwd_kernel<ND, CM, 4, true><<<grid, 256, 0, st>>>(src, flow, out, idx, g);
-    else      warp_fwd_kernel<ND, CM, 1, true><<<grid, 256, 0, st>>>(src, flow, out, idx, g);
+    if (vec4) WARP_LAUNCH(4, true); else WARP_LAUNCH(1, true);
   } else {
-    if (vec4) warp_fwd_kernel<ND, CM, 4, false><<<grid, 256, 0, st>>>(src, flow, out, idx, g);
-    else      warp_fwd_kernel<ND, CM, 1, false><<<grid, 256, 0, st>>>(src, flow, out, idx, g);
+    if (vec4) WARP_LAUNCH(4, false); else WARP_LAUNCH(1, false);
   }
+#undef WARP_LAUNCH
   DFMIR_CHECK_LAUNCH("dfmir_warp_fwd");
   return DFMIR_OK;
 }
@@ -346,8 +352,14 @@ extern "C" int dfmir_warp_bwd(const float* grad_out, const float* src, const flo
   const long long items = (long long)g.B * g.nvox;
   if (items == 0) return DFMIR_OK;
   const int grid = grid_for(items, 256);
-  DISPATCH_ND_CM(nd, coord_mode,
-                 (warp_bwd_kernel<ND, CM><<<grid, 256, 0, st>>>(grad_out, src, flow, d_src, d_flow, g)));
+  const bool narrow = (long long)g.B * g.nvox * (g.C > nd ? g.C : nd) < (1LL << 31);
+  if (narrow) {
+    DISPATCH_ND_CM(nd, coord_mode,
+                   (warp_bwd_kernel<ND, CM, int><<<grid, 256, 0, st>>>(grad_out, src, flow, d_src, d_flow, g)));
+  } else {
+    DISPATCH_ND_CM(nd, coord_mode,
+                   (warp_bwd_kernel<ND, CM, long long><<<grid, 256, 0, st>>>(grad_out, src, flow, d_src, d_flow, g)));
+  }
   DFMIR_CHECK_LAUNCH("dfmir_warp_bwd");
   return DFMIR_OK;
 }
@@ -372,8 +384,13 @@ extern "C" int dfmir_vecint_fwd(const float* vel, float* steps, int B, int nd, c
     float* out = steps + (long long)(keep_all ? k : k & 1) * slab;
     const int B_in = k == 0 ? B : Bv;
     const float lo = k == 0 ? sc : 1.f, hi = k == 0 ? -sc : 1.f;
-    DISPATCH_ND_CM(nd, coord_mode,
-                   (vecint_step_kernel<ND, CM><<<grid, 256, 0, st>>>(in, out, B_in, Bv, lo, hi, g)));
+    if (slab < (1LL << 31)) {
+      DISPATCH_ND_CM(nd, coord_mode,
+                     (vecint_step_kernel<ND, CM, int><<<grid, 256, 0, st>>>(in, out, B_in, Bv, lo, hi, g)));
+    } else {
+      DISPATCH_ND_CM(nd, coord_mode,
+                     (vecint_step_kernel<ND, CM, long long><<<grid, 256, 0, st>>>(in, out, B_in, Bv, lo, hi, g)));
+    }
     DFMIR_CHECK_LAUNCH("dfmir_vecint_fwd");
   }
   return DFMIR_OK;
@@ -402,8 +419,13 @@ extern "C" int dfmir_vecint_bwd(const float* grad_out, const float* vel, const f
     const int B_in = k == 0 ? B : Bv;
     const float lo = k == 0 ? sc : 1.f, hi = k == 0 ? -sc : 1.f;
     DFMIR_CUDA(cudaMemsetAsync(gin, 0, sizeof(float) * (k == 0 ? (long long)B * nd * g.nvox : slab), st));
-    DISPATCH_ND_CM(nd, coord_mode,
-                   (vecint_step_bwd_kernel<ND, CM><<<grid, 256, 0, st>>>(gcur, in, gin, B_in, Bv, lo, hi, g)));
+    if (slab < (1LL << 31)) {
+      DISPATCH_ND_CM(nd, coord_mode,
+                     (vecint_step_bwd_kernel<ND, CM, int><<<grid, 256, 0, st>>>(gcur, in, gin, B_in, Bv, lo, hi, g)));
+    } else {
+      DISPATCH_ND_CM(nd, coord_mode,
+                     (vecint_step_bwd_kernel<ND, CM, long long><<<grid, 256, 0, st>>>(gcur, in, gin, B_in, Bv, lo, hi, g)));
+    }
     DFMIR_CHECK_LAUNCH("dfmir_vecint_bwd");
     gcur = gin;
   }

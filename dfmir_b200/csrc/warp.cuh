@@ -24,7 +24,8 @@ __device__ __forceinline__ float dfmir_unnorm_coord(int i, float f, int S) {
   else
     q = __fmul_rn(loc, __fdiv_rn(1.0f, sm1));
   const float n = __fmul_rn(2.0f, __fsub_rn(q, 0.5f));
-  return __fmul_rn(__fdiv_rn(__fadd_rn(n, 1.0f), 2.0f), sm1);
+  // (n + 1) / 2: multiplying by 0.5 is the same correctly-rounded value as dividing by 2, at a tenth of the cost
+  return __fmul_rn(__fmul_rn(__fadd_rn(n, 1.0f), 0.5f), sm1);
 }
 
 // float -> int that is safe for NaN / huge values (maps them far out of bounds).
