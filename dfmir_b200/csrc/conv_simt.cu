@@ -302,6 +302,94 @@ conv_wgrad_simt_kernel(const float* __restrict__ x, const float* __restrict__ dy
   if (db && blockIdx.x == 0 && t < BN && n0 + t < p.Cout) atomicAdd(db + n0 + t, bacc);
 }
 
+// ------------------------------------------------------------------ weight gradient, few output channels
+// Cout <= CO (the VoxelMorph full-resolution layers: 34 -> 16 and the flow head 16 -> nd).  The GEMM view is
+// K x Cout with Cout tiny and M = millions of positions, so each thread owns ONE row k = (tap, ci) of dW with all
+// its CO accumulators in registers and walks the positions of its chunk: one coalesced x load (consecutive
+// threads = consecutive channels of a tap) feeds CO FMAs; the dy rows of a batch of positions are staged in shared
+// memory and read as broadcast float4.  Position chunks over gridDim.x, combined with fp32 atomics.
+template <int CO, int PB>
+__global__ void __launch_bounds__(256)
+conv_wgrad_fewco_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                        float* __restrict__ db, ConvP p, long long chunk) {
+  __shared__ __align__(16) float gs[PB][CO];
+  __shared__ long long xbase[PB];
+  __shared__ int org[PB][3];
+  const int t = threadIdx.x;
+  const int k = blockIdx.y * 256 + t;
+  const bool kin = k < p.K;
+  int tz = 0, ty = 0, tx = 0, ci = 0;
+  if (kin) {
+    int tap = k / p.Cin;
+    ci = k - tap * p.Cin;
+    tx = tap % p.Kk[2]; tap /= p.Kk[2];
+    ty = tap % p.Kk[1]; tz = tap / p.Kk[1];
+  }
+  const long long mbeg = (long long)blockIdx.x * chunk;
+  const long long mend = min(p.M, mbeg + chunk);
+  float acc[CO];
+#pragma unroll
+  for (int j = 0; j < CO; ++j) acc[j] = 0.f;
+  float bacc = 0.f;
+  for (long long mb = mbeg; mb < mend; mb += PB) {
+    __syncthreads();
+    for (int e = t; e < PB * CO; e += 256) {
+      const int r = e / CO, c = e - r * CO;
+      const long long m = mb + r;
+      float v = 0.f;
+      if (m < mend && c < p.Cout) {
+        long long q = m;
+        const int ox = (int)(q % p.O[2]); q /= p.O[2];
+        const int oy = (int)(q % p.O[1]); q /= p.O[1];
+        const int oz = (int)(q % p.O[0]); q /= p.O[0];
+        v = __ldg(dy + q * p.ys[0] + oz * p.ys[1] + oy * p.ys[2] + ox * p.ys[3] + c * p.ys[4]);
+      }
+      gs[r][c] = v;
+    }
+    if (t < PB) {
+      const long long m = mb + t;
+      if (m < mend) {
+        long long q = m;
+        const int ox = (int)(q % p.O[2]); q /= p.O[2];
+        const int oy = (int)(q % p.O[1]); q /= p.O[1];
+        const int oz = (int)(q % p.O[0]); q /= p.O[0];
+        xbase[t] = q * p.xs[0];
+        org[t][0] = oz * p.stride - p.pad[0]; org[t][1] = oy * p.stride - p.pad[1]; org[t][2] = ox * p.stride - p.pad[2];
+      } else {
+        xbase[t] = -1; org[t][0] = org[t][1] = org[t][2] = 0;
+      }
+    }
+    __syncthreads();
+    if (kin) {
+#pragma unroll 4
+      for (int r = 0; r < PB; ++r) {
+        const long long base = xbase[r];
+        const int iz = org[r][0] + tz, iy = org[r][1] + ty, ix = org[r][2] + tx;
+        float xv = 0.f;
+        if (base >= 0 && iz >= 0 && iz < p.I[0] && iy >= 0 && iy < p.I[1] && ix >= 0 && ix < p.I[2])
+          xv = __ldg(x + base + iz * p.xs[1] + iy * p.xs[2] + ix * p.xs[3] + ci * p.xs[4]);
+        const float4* g4 = reinterpret_cast<const float4*>(gs[r]);
+#pragma unroll
+        for (int j = 0; j < CO / 4; ++j) {
+          const float4 g = g4[j];
+          acc[4 * j] = fmaf(xv, g.x, acc[4 * j]); acc[4 * j + 1] = fmaf(xv, g.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(xv, g.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(xv, g.w, acc[4 * j + 3]);
+        }
+      }
+    }
+    if (db && blockIdx.y == 0 && t < CO) {
+#pragma unroll 4
+      for (int r = 0; r < PB; ++r) bacc += gs[r][t];
+    }
+  }
+  if (kin) {
+#pragma unroll
+    for (int j = 0; j < CO; ++j)
+      if (j < p.Cout) atomicAdd(dw + (long long)k * p.Cout + j, acc[j]);
+  }
+  if (db && blockIdx.y == 0 && t < p.Cout && t < CO) atomicAdd(db + t, bacc);
+}
+
 // dx = dy * act'(y) on contiguous arrays (LeakyReLU(0.2) / tanh / ReLU of a conv epilogue)
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, long long n,
@@ -412,6 +500,19 @@ extern "C" int dfmir_conv_wgrad(const float* x, const float* dy, float* dw, floa
   if (p.M == 0) return DFMIR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (dfmir_thin_wgrad(x, dy, dw, db, d, st, &rc)) return rc;
+  if (p.Cout <= 16 && p.M >= 4096) {
+    // few output channels, many positions: one dW row per thread (see conv_wgrad_fewco_kernel)
+    const int gy = (p.K + 255) / 256;
+    long long blocks = (8LL * dfmir_num_sms() + gy - 1) / gy;
+    long long chunk = (p.M + blocks - 1) / blocks;
+    chunk = (chunk + 31) / 32 * 32;
+    if (chunk < 256) chunk = 256;
+    const unsigned gxf = (unsigned)((p.M + chunk - 1) / chunk);
+    if (p.Cout <= 4) conv_wgrad_fewco_kernel<4, 32><<<dim3(gxf, gy), 256, 0, st>>>(x, dy, dw, db, p, chunk);
+    else conv_wgrad_fewco_kernel<16, 32><<<dim3(gxf, gy), 256, 0, st>>>(x, dy, dw, db, p, chunk);
+    DFMIR_CHECK_LAUNCH("dfmir_conv_wgrad(few output channels)");
+    return DFMIR_OK;
+  }
   constexpr int BKD = 64, BR = 16;
   const int gx = (p.K + BKD - 1) / BKD;
   auto splits_for = [&](int gy) {

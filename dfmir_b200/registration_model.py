@@ -7,6 +7,9 @@ unchanged; every tensor op of the step runs in libdfmir_b200.so.
 Differences from the reference, all at the host level:
   * `feat_k` encoder passes run under no_grad (the reference builds and discards their graph:
     patchnce.py:17 detaches k);
+  * `feat_k` for real_A / real_B is tapped from the full generator pass of forward() (same values, the
+    encoder is deterministic and InstanceNorm per-sample) instead of being recomputed by three more
+    encoder passes (DFMIR_REUSE_REAL_FEATURES=0 restores the reference's schedule);
   * the two masked-L1 terms fuse the mask construction (registration_model.py:160-161) into the
     loss kernel and return a device scalar 0 for an empty mask instead of forcing a host sync
     (`torch.sum(mask) == 0`, :259);
@@ -43,6 +46,10 @@ def default_options(**overrides):
         setattr(opt, k, v)
     return opt
 
+
+# feat_k of real_A / real_B taken from the full generator pass instead of three extra encoder passes
+# (identical values; DFMIR_REUSE_REAL_FEATURES=0 restores the reference's schedule pass for pass)
+REUSE_REAL_FEATURES = os.environ.get("DFMIR_REUSE_REAL_FEATURES", "1") != "0"
 
 _test_image_cache = {}
 
@@ -173,7 +180,7 @@ class BaseModel:
         return OrderedDict((name, getattr(self, name)) for name in self.visual_names)
 
     def get_current_losses(self):
-        return OrderedDict((name, float(getattr(self, 'loss_' + name))) for name in self.loss_names)
+        return OrderedDict((name, float(getattr(self, 'loss_' + name).detach() if torch.is_tensor(getattr(self, 'loss_' + name)) else getattr(self, 'loss_' + name))) for name in self.loss_names)
 
     def save_networks(self, epoch):
         os.makedirs(self.save_dir, exist_ok=True)
@@ -292,7 +299,17 @@ class REGISTRATIONModel(BaseModel):
             self.flipped_for_equivariance = self.opt.isTrain and (np.random.random() < 0.5)
             if self.flipped_for_equivariance:
                 self.real = torch.flip(self.real, [3])
-        self.fake = self.netG(self.real)
+        # The full pass over cat(real_A, real_B) already computes the encoder activations the reference
+        # recomputes three times as feat_k = netG(real_A / real_B, nce_layers, encode_only=True)
+        # (registration_model.py:244; InstanceNorm is per-sample, so the values are the same): tap them
+        # here and reuse them, detached, as PatchNCELoss detaches k anyway (patchnce.py:17).
+        self._real_feats = None
+        flipped = self.opt.flip_equivariance and getattr(self, 'flipped_for_equivariance', False)
+        if self.isTrain and REUSE_REAL_FEATURES and not flipped:
+            self.fake, feats = self.netG(self.real, list(self.nce_layers))
+            self._real_feats = [f.detach() for f in feats]
+        else:
+            self.fake = self.netG(self.real)
         self.fake_B = self.fake[:self.real_A.size(0)]
         self.idt_B = self.fake[self.real_A.size(0):]
 
@@ -317,7 +334,13 @@ class REGISTRATIONModel(BaseModel):
             feat_q = [torch.flip(fq, [3]) for fq in feat_q]
         mlp_ready = (not self.netF.use_mlp) or self.netF.mlp_init
         with torch.no_grad():   # k is detached inside PatchNCELoss (patchnce.py:17)
-            feat_k = self.netG(src, self.nce_layers, encode_only=True)
+            B = self.real_A.size(0)
+            if self._real_feats is not None and src is self.real_A:
+                feat_k = [f[:B] for f in self._real_feats]
+            elif self._real_feats is not None and src is self.real_B:
+                feat_k = [f[B:] for f in self._real_feats]
+            else:
+                feat_k = self.netG(src, self.nce_layers, encode_only=True)
             if not mlp_ready:
                 self.netF.create_mlp(feat_k)
             feat_k_pool, sample_ids = self.netF(feat_k, self.opt.num_patches, patch_ids)

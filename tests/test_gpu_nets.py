@@ -60,6 +60,10 @@ CONV_CASES = [  # nd, N, Cin, Cout, spatial, k, stride, pad, act, planar
     (2, 2, 1, 64, (45, 76), 7, 1, 0, 0, False),     # stem at full width: several (partial) tiles of the direct kernels
     (2, 1, 64, 1, (76, 45), 7, 1, 0, 2, False),     # head at full width
     (2, 1, 1, 24, (40, 40), 7, 1, 3, 0, False),     # zero-padded thin conv
+    (2, 1, 34, 16, (64, 64), 3, 1, 1, 1, False),    # few output channels, >= 4096 positions: one-row-per-thread wgrad
+    (2, 2, 16, 2, (48, 64), 3, 1, 1, 0, True),      # flow head at size (planar output)
+    (3, 1, 18, 3, (16, 16, 20), 3, 1, 1, 0, True),  # 3-D flow head
+    (2, 2, 2, 16, (96, 96), 3, 2, 1, 1, False),     # strided first encoder layer
 ]
 
 
