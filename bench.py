@@ -236,6 +236,8 @@ def run_ours(args):
                    "conv_engine": Fn.CONV_ENGINE, "arithmetic": "fp32 storage; convolutions with 64..256 channels on tcgen05 "
                    "kind::tf32 (operands truncated to TF32, fp32 accumulate: the class cuDNN runs the reference in); "
                    "every other kernel fp32",
+                   "schedule": "feat_k of real_A / real_B tapped from the full generator pass (identical values; the reference "
+                               "recomputes them with 3 more encoder passes) - DFMIR_REUSE_REAL_FEATURES=0 restores that",
                    "l2_policy": "inputs larger than L2: each step streams > 10 GB of activations (L2 is 126 MB)"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -262,6 +264,111 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ours_3d(args):
+    """BASELINE configs[2]: VoxelMorph-3D (6-level features) on 128^3 volume pairs, batch 2 per GPU: U-Net fwd,
+    fused integrate -> resize -> warp -> NCC + Grad (one cooperative launch), backward, Adam.  Weak scaling."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from dfmir_b200 import _lib, vxm
+    B, S = args.batch3d, args.size3d
+    torch.manual_seed(1234)
+    R = vxm.VxmDense((S, S, S), [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]], int_steps=7, bidir=False).cuda()
+    params = [p for p in R.parameters() if p.requires_grad]
+    flat = None
+    if world > 1:
+        for t in list(R.parameters()) + list(R.buffers()):
+            dist.broadcast(t.data, src=0)
+        flat = torch.zeros(sum(p.numel() for p in params), device="cuda")
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p); off += p.numel()
+    optim = torch.optim.Adam(params, lr=2e-4, betas=(0.5, 0.999))
+    g = torch.Generator().manual_seed(77 + rank)
+    def vol():
+        x = torch.randn(B, 1, S, S, S, generator=g)
+        k = torch.ones(1, 1, 5, 5, 5) / 125.0
+        for _ in range(2):
+            x = torch.nn.functional.conv3d(x, k, padding=2)
+        return torch.tanh(3 * x / x.std()).contiguous().pin_memory()
+    hA, hB = vol(), vol()
+    state = {"A": hA.cuda(), "B": hB.cuda(), "loss": None}
+
+    def step_resident():
+        if flat is not None:
+            flat.zero_()
+        else:
+            optim.zero_grad(set_to_none=False) if params[0].grad is not None else None
+        y, flow, ncc, grad = R.forward_with_losses(state["A"], state["B"], win=9)
+        loss = ncc + 0.02 * grad
+        loss.backward()
+        if flat is not None:
+            dist.all_reduce(flat); flat.mul_(1.0 / world)
+        optim.step()
+        state["loss"] = loss.detach()
+
+    def step_e2e():
+        state["A"] = hA.cuda(non_blocking=True); state["B"] = hB.cuda(non_blocking=True)
+        step_resident()
+        float(state["loss"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.launch_count_reset()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    flops = 284.6e9 * B      # SURVEY 8d: VxmDense-3D 128^3 6-level, fwd 95.0 + bwd 189.6 GFLOP per pair
+    pk, pk_src = peaks()
+    line = {
+        "metric": METRIC, "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"3D {S}^3 batch={B}/GPU VoxelMorph-3D (6-level) + VecInt + NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[2])",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "arithmetic": "fp32 CUDA cores (the 2..64-channel 3-D convolutions have no tensor-core kernel yet)",
+                   "l2_policy": "inputs larger than L2: full-resolution activations are 34 channels x 8 MB per volume"},
+        "clocks": clocks,
+        "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(2 * B * S ** 3 * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "conv_simt_kernel / conv_wgrad_simt_kernel (fp32 implicit GEMM, all layers of the step)",
+                     "achieved": flops * args.steps / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": flops * args.steps / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+                     "peak_source": f"bf16_tflops_sustained, {pk_src}; whole-step algorithmic conv FLOPs over step time (not a single kernel)",
+                     "traffic": None},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -271,6 +378,10 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="pairs per GPU per step")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--workload", default="2d", choices=["2d", "3d"],
+                    help="2d: BASELINE configs[1] (the headline line, default); 3d: configs[2], VoxelMorph-3D 128^3")
+    ap.add_argument("--batch3d", type=int, default=2)
+    ap.add_argument("--size3d", type=int, default=128)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -279,7 +390,10 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the dfmir_b200 path has no CPU fallback (use --impl reference for the CPU arm)")
-    run_ours(args)
+    if args.workload == "3d":
+        run_ours_3d(args)
+    else:
+        run_ours(args)
 
 
 if __name__ == "__main__":

@@ -1,10 +1,12 @@
-// K1 (tensor-core path): 2-D stride-1 convolution as an implicit GEMM on the 5th-generation tensor
+// K1 / K2 (tensor-core path): 2-D and 3-D stride-1 convolution as an implicit GEMM on the 5th-generation tensor
 // cores — tcgen05.mma (kind::tf32, fp32 accumulators in TMEM), operands staged in shared memory by
 // TMA, persistent CTAs (one per SM) that each walk a list of output tiles.
 //
 // Replaces the cuDNN implicit-GEMM engines behind nn.Conv2d in ResnetGenerator
-// (models/networks.py:995,1016 and the 18 ResnetBlock convs :1201,1214) for the layers whose
-// channel counts fill a tensor-core tile (Cin % 32 == 0, Cout in {64,128,256}).  The reference's
+// (models/networks.py:995,1016 and the 18 ResnetBlock convs :1201,1214) and behind the stride-1
+// nn.Conv2d / nn.Conv3d of VoxelMorph's U-Net (vxm networks.py:1515,1077).  Any output channel count
+// (tile widths 16..128, missing channels are zero-filled weight rows), reduction-side channel counts
+// that are multiples of 4 (a partial 32-channel chunk is zero-filled by the TMA unit).  The reference's
 // own CUDA path runs these in TF32 (cuDNN default); this kernel does the same arithmetic class:
 // fp32 storage, TF32 operands (the tensor core truncates fp32 to 10 mantissa bits), fp32 accumulate.
 //
@@ -41,14 +43,14 @@ constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 struct UmmaP {
-  int N, H, W;            // output sample count and spatial size
-  int Cin, Cout;
-  int KH, KW, pad_h, pad_w;
-  int TW, TH, tiles_w, tiles_h;
-  int ptiles;             // N * tiles_h * tiles_w sub-tiles of 128 pixels
-  int flip;               // 1: use tap (KH*KW-1-t) of the weight tensor (data gradient)
+  int N, D, H, W;         // output sample count and spatial size (2-D: D = 1)
+  int Cin, Cout;          // K-side / N-side channel counts of this product
+  int KD, KH, KW, pad_d, pad_h, pad_w;
+  int TD, TH, TW, tiles_d, tiles_h, tiles_w;
+  int ptiles;             // N * tiles_d * tiles_h * tiles_w sub-tiles of 128 voxels
+  int flip;               // 1: use tap (taps-1-t) of the weight tensor (data gradient)
   int act;
-  long long ys[4];        // output element strides n, h, w, c
+  long long ys[5];        // output element strides n, d, h, w, c
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -56,6 +58,25 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == DFMIR_ACT_TANH) return tanhf(v);
   if (act == DFMIR_ACT_RELU) return v > 0.f ? v : 0.f;
   return v;
+}
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 template <int BN, int MT, int STAGES, int AS>
@@ -73,6 +94,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const float* __restrict__ bias, float* __restrict__ y, const UmmaP p) {
   using L = SmemLayout<BN, MT, STAGES, AS>;
+  constexpr int CW = BN < 32 ? BN : 32;       // accumulator columns per TMEM load
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-byte aligned
   uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
@@ -82,13 +104,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + AS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.Cout / BN;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
   const int pgroups = (p.ptiles + MT - 1) / MT;
   const int items = pgroups * n_tiles;
-  const int cchunks = p.Cin / KCH;
-  const int taps = p.KH * p.KW;
+  const int cchunks = (p.Cin + KCH - 1) / KCH;   // a partial last chunk is zero-filled by the TMA unit
+  const int taps = p.KD * p.KH * p.KW;
   const int num_kb = taps * cchunks;
-  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const int tiles_hw = p.tiles_h * p.tiles_w;
+  const int tiles_per_img = p.tiles_d * tiles_hw;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -108,27 +131,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int nt = item % n_tiles, pg = item / n_tiles;
-        int sn[MT], sh[MT], sw[MT];
+        int sn[MT], sd[MT], sh[MT], sw[MT];
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
           const int pt = pg * MT + j;
           if (pt < p.ptiles) {
-            const int n = pt / tiles_per_img, rem = pt - n * tiles_per_img;
+            const int n = pt / tiles_per_img; int rem = pt - n * tiles_per_img;
+            const int td_i = rem / tiles_hw; rem -= td_i * tiles_hw;
             const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
-            sn[j] = n; sh[j] = th_i * p.TH; sw[j] = tw_i * p.TW;
-          } else { sn[j] = p.N; sh[j] = 0; sw[j] = 0; }      // beyond the batch: the TMA unit zero-fills
+            sn[j] = n; sd[j] = td_i * p.TD; sh[j] = th_i * p.TH; sw[j] = tw_i * p.TW;
+          } else { sn[j] = p.N; sd[j] = 0; sh[j] = 0; sw[j] = 0; }      // beyond the batch: the TMA unit zero-fills
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(empty + s, ph ^ 1);
           const int tap = kb / cchunks, cc = kb - tap * cchunks;
-          const int r = tap / p.KW, q = tap - r * p.KW;
+          const int q = tap % p.KW; const int t2 = tap / p.KW;
+          const int r = t2 % p.KH, kd = t2 / p.KH;
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           mbar_expect_tx(full + s, (uint32_t)L::STAGE_BYTES);
 #pragma unroll
           for (int j = 0; j < MT; ++j)
-            tma_load_4d(sa + j * A_BYTES, &tmA, full + s, cc * KCH, sw[j] + q - p.pad_w, sh[j] + r - p.pad_h, sn[j]);
+            tma_load_5d(sa + j * A_BYTES, &tmA, full + s, cc * KCH, sw[j] + q - p.pad_w, sh[j] + r - p.pad_h,
+                        sd[j] + kd - p.pad_d, sn[j]);
           tma_load_3d(sa + MT * A_BYTES, &tmB, full + s, cc * KCH, nt * BN, p.flip ? taps - 1 - tap : tap);
         }
       }
@@ -170,7 +196,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;            // hardware rule: a warp may access TMEM lanes 32*(warp%4)..+31
     const int jfirst = e >> 2;
     const int row = quarter * 32 + lane;
-    const int th = row / p.TW, tw = row - th * p.TW;
+    const int thw = p.TH * p.TW;
+    const int td = row / thw, th = (row - td * thw) / p.TW, tw = row % p.TW;
+    const bool vec_ok = p.ys[4] == 1 && (p.Cout & 3) == 0;
     uint32_t ti = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
       const uint32_t as = ti % AS, aph = (ti / AS) & 1;
@@ -181,30 +209,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int j = jfirst; j < MT; j += EPI_WARPS / 4) {
         const int pt = pg * MT + j;
-        const int n = pt / tiles_per_img, rem = pt - n * tiles_per_img;
+        const int n = pt / tiles_per_img; int rem = pt - n * tiles_per_img;
+        const int td_i = rem / tiles_hw; rem -= td_i * tiles_hw;
         const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
-        const int oh = th_i * p.TH + th, ow = tw_i * p.TW + tw;
-        const bool valid = pt < p.ptiles && oh < p.H && ow < p.W;
-        float* yp = y + (long long)n * p.ys[0] + (long long)oh * p.ys[1] + (long long)ow * p.ys[2];
+        const int od = td_i * p.TD + td, oh = th_i * p.TH + th, ow = tw_i * p.TW + tw;
+        const bool valid = pt < p.ptiles && od < p.D && oh < p.H && ow < p.W;
+        float* yp = y + (long long)n * p.ys[0] + (long long)od * p.ys[1] + (long long)oh * p.ys[2] + (long long)ow * p.ys[3];
         const uint32_t acc = tmem_base + as * (MT * BN) + j * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tmem_ld_32x32(acc + (uint32_t)c0, v);
-          if (valid) {
+        for (int c0 = 0; c0 < BN; c0 += CW) {
+          float v[CW];
+          if (CW == 32) tmem_ld_32x32(acc + (uint32_t)c0, v); else tmem_ld_32x16(acc + (uint32_t)c0, v);
+          if (valid && n0 + c0 < p.Cout) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < CW; ++i) {
               float t = v[i];
-              if (bias) t += __ldg(bias + n0 + c0 + i);
+              if (bias && n0 + c0 + i < p.Cout) t += __ldg(bias + n0 + c0 + i);
               v[i] = act_apply(t, p.act);
             }
-            if (p.ys[3] == 1) {
+            if (vec_ok && n0 + c0 + CW <= p.Cout) {
               float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) yp[(long long)(n0 + c0 + i) * p.ys[3]] = v[i];
+              for (int i = 0; i < CW; ++i)
+                if (n0 + c0 + i < p.Cout) yp[(long long)(n0 + c0 + i) * p.ys[4]] = v[i];
             }
           }
         }
@@ -220,35 +250,71 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ---------------------------------------------------------------- host side
-int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
-  if (!d) { dfmir_set_error("%s: null descriptor", who); return DFMIR_ERR_ARG; }
-  if (d->nd != 2 || d->stride != 1) { dfmir_set_error("%s: tensor-core path covers 2-D stride-1 convolutions", who); return DFMIR_ERR_UNSUPPORTED; }
+// strides arrive as {n, spatial[nd], c}
+struct Strides5 { long long n, d, h, w, c; };
+Strides5 spread(const long long* s, int nd) {
+  Strides5 r;
+  r.n = s[0]; r.c = s[nd + 1];
+  if (nd == 3) { r.d = s[1]; r.h = s[2]; r.w = s[3]; } else { r.h = s[1]; r.w = s[2]; r.d = 0; }
+  return r;
+}
+
+bool operand_ok(const long long* s, int nd) {     // TMA source: unit channel stride, 16-byte multiples elsewhere
+  if (s[nd + 1] != 1) return false;
+  for (int i = 0; i <= nd; ++i) if (s[i] & 3) return false;
+  return true;
+}
+
+int umma_shape_ok(const dfmir_conv_desc* d, int dgrad) {
+  if (!d || (d->nd != 2 && d->nd != 3) || d->stride != 1) return 0;
   const int Cin = dgrad ? d->Cout : d->Cin, Cout = dgrad ? d->Cin : d->Cout;
-  if (Cin % KCH || !(Cout == 64 || Cout == 128 || Cout == 256)) {
-    dfmir_set_error("%s: needs Cin %% 32 == 0 and Cout in {64,128,256} (got %d -> %d)", who, Cin, Cout);
+  // K side: rows of the weight matrix must be 16-byte multiples (Cin % 4), at least half a 32-channel chunk
+  // of useful work; N side: any count (padded to the tile by zero-filled weight rows)
+  if (Cin % 4 || Cin < 16 || Cout < 1) return 0;
+  const long long* is = dgrad ? d->y_strides : d->x_strides;
+  if (!operand_ok(is, d->nd)) return 0;
+  for (int a = 0; a < d->nd; ++a) {
+    const int pd = dgrad ? d->kernel[a] - 1 - d->pad[a] : d->pad[a];
+    if (pd < 0) return 0;
+  }
+  return 1;
+}
+
+int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
+  if (!umma_shape_ok(d, dgrad)) {
+    dfmir_set_error("%s: the tensor-core path covers 2-D / 3-D stride-1 convolutions whose reduction-side channel count is a "
+                    "multiple of 4 and >= 16, on channels-last operands with 16-byte aligned strides", who);
     return DFMIR_ERR_UNSUPPORTED;
   }
-  p.N = d->N; p.Cin = Cin; p.Cout = Cout;
-  p.KH = d->kernel[0]; p.KW = d->kernel[1];
+  const int nd = d->nd, sh = 3 - nd;
+  p.N = d->N; p.Cin = dgrad ? d->Cout : d->Cin; p.Cout = dgrad ? d->Cin : d->Cout;
+  int K[3] = {1, 1, 1}, P[3] = {0, 0, 0}, O[3] = {1, 1, 1};
   const int* osh = dgrad ? d->in_shape : d->out_shape;
-  p.H = osh[0]; p.W = osh[1];
-  p.pad_h = dgrad ? d->kernel[0] - 1 - d->pad[0] : d->pad[0];
-  p.pad_w = dgrad ? d->kernel[1] - 1 - d->pad[1] : d->pad[1];
-  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act;
-  const long long* os = dgrad ? d->x_strides : d->y_strides;
-  for (int i = 0; i < 4; ++i) p.ys[i] = os[i];
-  // tile rectangle TH x TW = 128 pixels (powers of two, TW >= 8): the shape that wastes the fewest
-  // pixels on partial tiles (66x66 data-gradient outputs: 16x8 covers 76 % vs 52 % for 64x2); ties go to
-  // the widest tile (longest contiguous runs per TMA box row)
-  long long best = -1;
-  for (int TW = 128; TW >= 8; TW >>= 1) {
-    const int TH = BM / TW;
-    const long long area = (long long)((p.W + TW - 1) / TW) * TW * ((p.H + TH - 1) / TH) * TH;
-    if (best < 0 || area < best) { best = area; p.TW = TW; p.TH = TH; }
+  for (int a = 0; a < nd; ++a) {
+    K[a + sh] = d->kernel[a];
+    P[a + sh] = dgrad ? d->kernel[a] - 1 - d->pad[a] : d->pad[a];
+    O[a + sh] = osh[a];
   }
+  p.KD = K[0]; p.KH = K[1]; p.KW = K[2]; p.pad_d = P[0]; p.pad_h = P[1]; p.pad_w = P[2];
+  p.D = O[0]; p.H = O[1]; p.W = O[2];
+  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act;
+  const Strides5 os = spread(dgrad ? d->x_strides : d->y_strides, nd);
+  p.ys[0] = os.n; p.ys[1] = os.d; p.ys[2] = os.h; p.ys[3] = os.w; p.ys[4] = os.c;
+  // tile box TD x TH x TW = 128 voxels (powers of two, TW >= 8): the shape that wastes the fewest voxels on
+  // partial tiles (66x66 data-gradient outputs: 16x8 covers 76 % vs 52 % for 64x2); ties go to the widest
+  // tile (longest contiguous runs per TMA box row)
+  long long best = -1;
+  for (int TW = 128; TW >= 8; TW >>= 1)
+    for (int TH = BM / TW; TH >= 1; TH >>= 1) {
+      const int TD = BM / (TW * TH);
+      if (TD > 1 && nd == 2) continue;
+      const long long vol = (long long)((p.W + TW - 1) / TW) * TW * ((p.H + TH - 1) / TH) * TH * ((p.D + TD - 1) / TD) * TD;
+      if (best < 0 || vol < best) { best = vol; p.TW = TW; p.TH = TH; p.TD = TD; }
+    }
   p.tiles_w = (p.W + p.TW - 1) / p.TW;
   p.tiles_h = (p.H + p.TH - 1) / p.TH;
-  p.ptiles = p.N * p.tiles_h * p.tiles_w;
+  p.tiles_d = (p.D + p.TD - 1) / p.TD;
+  p.ptiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w;
   return DFMIR_OK;
 }
 
@@ -257,7 +323,7 @@ int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
                 const char* who) {
   using L = SmemLayout<BN, MT, STAGES, AS>;
   DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BN, MT, STAGES, AS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-  const int items = ((p.ptiles + MT - 1) / MT) * (p.Cout / BN);
+  const int items = ((p.ptiles + MT - 1) / MT) * ((p.Cout + BN - 1) / BN);
   if (items == 0) return DFMIR_OK;
   // persistent CTAs, one per SM; with fewer items than SMs every item gets its own CTA
   int grid = dfmir_num_sms();
@@ -270,28 +336,28 @@ int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
   return DFMIR_OK;
 }
 
-// act: source activation (channels-last, element strides {n,h,w,c}, c stride 1) of spatial size (IH, IW)
-int run_umma(const float* act, const long long* as, int IH, int IW, const float* w, const float* bias, float* y,
+// act: source activation (channels-last, c stride 1) with element strides `as` and spatial size (ID, IH, IW)
+int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const float* w, const float* bias, float* y,
              const UmmaP& p, cudaStream_t st, const char* who) {
   static const int cfg = getenv("DFMIR_UMMA_CFG") ? atoi(getenv("DFMIR_UMMA_CFG")) : 0;   // tuning experiments
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
-  if (as[3] != 1 || ((uintptr_t)act & 15) || (as[0] & 3) || (as[1] & 3) || (as[2] & 3) || ((uintptr_t)w & 15)) {
-    dfmir_set_error("%s: TMA needs unit channel stride and 16-byte aligned rows", who); return DFMIR_ERR_ARG;
-  }
+  if (((uintptr_t)act & 15) || ((uintptr_t)w & 15)) { dfmir_set_error("%s: TMA needs 16-byte aligned base pointers", who); return DFMIR_ERR_ARG; }
+  int BN = p.Cout <= 16 ? 16 : (p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : 128));
+  if (p.Cout == 256 && (cfg == 1 || cfg == 5)) BN = 256;
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)p.N};
-    cuuint64_t strides[3] = {(cuuint64_t)as[2] * 4, (cuuint64_t)as[1] * 4, (cuuint64_t)as[0] * 4};
-    cuuint32_t box[4] = {KCH, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const long long sd = ID > 1 ? as.d : as.h * IH;      // 2-D: a depth axis of extent 1 (its stride is never used)
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)ID, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)as.w * 4, (cuuint64_t)as.h * 4, (cuuint64_t)sd * 4, (cuuint64_t)as.n * 4};
+    cuuint32_t box[5] = {KCH, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TD, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(activation) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
   }
   {
-    const int taps = p.KH * p.KW;
-    const int BN = (p.Cout == 256 && cfg != 1 && cfg != 5) ? 128 : (p.Cout > 256 ? 256 : p.Cout);
+    const int taps = p.KD * p.KH * p.KW;
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
     cuuint32_t box[3] = {KCH, (cuuint32_t)BN, 1};
@@ -300,31 +366,22 @@ int run_umma(const float* act, const long long* as, int IH, int IW, const float*
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
   }
-  if (p.Cout == 256) {
-    // two 128-channel halves per pixel group: 48 KB stages x 4 and double-buffered accumulators beat one
-    // 256-wide tile (64 KB x 3, no epilogue overlap): 552 vs 430 TFLOP/s on the ResnetBlock conv at batch 32
-    if (cfg == 1) return launch_umma<256, 1, 4, 2>(tmA, tmB, bias, y, p, st, who);
-    if (cfg == 5) return launch_umma<256, 2, 3, 1>(tmA, tmB, bias, y, p, st, who);
+  // 128-channel tiles x 2 sub-tiles: 48 KB stages x 4 and double-buffered accumulators beat one 256-wide tile
+  // (64 KB x 3, no epilogue overlap): 552 vs 430 TFLOP/s on the ResnetBlock conv at batch 32
+  if (BN == 256) return cfg == 1 ? launch_umma<256, 1, 4, 2>(tmA, tmB, bias, y, p, st, who) : launch_umma<256, 2, 3, 1>(tmA, tmB, bias, y, p, st, who);
+  if (BN == 128) {
     if (cfg == 3) return launch_umma<128, 4, 2, 1>(tmA, tmB, bias, y, p, st, who);
     if (cfg == 4) return launch_umma<128, 1, 6, 2>(tmA, tmB, bias, y, p, st, who);
     return launch_umma<128, 2, 4, 2>(tmA, tmB, bias, y, p, st, who);
   }
-  if (p.Cout == 128) return launch_umma<128, 2, 4, 2>(tmA, tmB, bias, y, p, st, who);
-  return launch_umma<64, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
+  if (BN == 64) return launch_umma<64, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
+  if (BN == 32) return launch_umma<32, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
+  return launch_umma<16, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
 }
 
 }  // namespace
 
-extern "C" int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad) {
-  if (!d || d->nd != 2 || d->stride != 1) return 0;
-  const int Cin = dgrad ? d->Cout : d->Cin, Cout = dgrad ? d->Cin : d->Cout;
-  if (Cin % KCH || !(Cout == 64 || Cout == 128 || Cout == 256)) return 0;
-  const long long* is = dgrad ? d->y_strides : d->x_strides;
-  const long long* os = dgrad ? d->x_strides : d->y_strides;
-  if (is[3] != 1 || (is[0] & 3) || (is[1] & 3) || (is[2] & 3)) return 0;
-  if (os[3] == 1 && ((os[0] & 3) || (os[1] & 3) || (os[2] & 3))) return 0;
-  return 1;
-}
+extern "C" int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad) { return umma_shape_ok(d, dgrad); }
 
 // Forward on the tensor cores.  w: [tap][Cout][Cin] (Cin contiguous).
 extern "C" int dfmir_conv_umma_fwd(const float* x, const float* w, const float* bias, float* y,
@@ -333,7 +390,9 @@ extern "C" int dfmir_conv_umma_fwd(const float* x, const float* w, const float* 
   int rc = fill_umma(p, d, 0, "dfmir_conv_umma_fwd");
   if (rc) return rc;
   DFMIR_CHECK_ARG(x && w && y, "dfmir_conv_umma_fwd: null pointer");
-  return run_umma(x, d->x_strides, d->in_shape[0], d->in_shape[1], w, bias, y, p, (cudaStream_t)stream, "dfmir_conv_umma_fwd");
+  const int nd = d->nd;
+  return run_umma(x, spread(d->x_strides, nd), nd == 3 ? d->in_shape[0] : 1, d->in_shape[nd - 2], d->in_shape[nd - 1], w, bias, y, p,
+                  (cudaStream_t)stream, "dfmir_conv_umma_fwd");
 }
 
 // Data gradient on the tensor cores: dx = conv(dy, flipped taps, pad' = k-1-pad).
@@ -344,5 +403,7 @@ extern "C" int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx,
   int rc = fill_umma(p, d, 1, "dfmir_conv_umma_dgrad");
   if (rc) return rc;
   DFMIR_CHECK_ARG(dy && w && dx, "dfmir_conv_umma_dgrad: null pointer");
-  return run_umma(dy, d->y_strides, d->out_shape[0], d->out_shape[1], w, nullptr, dx, p, (cudaStream_t)stream, "dfmir_conv_umma_dgrad");
+  const int nd = d->nd;
+  return run_umma(dy, spread(d->y_strides, nd), nd == 3 ? d->out_shape[0] : 1, d->out_shape[nd - 2], d->out_shape[nd - 1], w, nullptr,
+                  dx, p, (cudaStream_t)stream, "dfmir_conv_umma_dgrad");
 }

@@ -538,11 +538,11 @@ blur_up_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, i
 }
 
 // ------------------------------------------------------------------ nearest x2 upsample + concat (U-Net skip)
-struct UcGeom { int N, nd, C1, C2; int S[3]; };  // S = full-resolution spatial dims (right-aligned)
+struct UcGeom { int N, nd, C1, C2; int S[3]; int Cs; };  // S = full-resolution spatial dims (right-aligned); Cs = channel stride of y (>= C1+C2, the rest zero)
 
 __global__ void __launch_bounds__(256)
 upcat_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, UcGeom g) {
-  const int C = g.C1 + g.C2;
+  const int C = g.Cs;
   const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
   const long long total = (long long)g.N * vox * C;
   const int L0 = g.S[0] > 1 ? g.S[0] / 2 : 1, L1 = g.S[1] / 2, L2 = g.S[2] / 2;
@@ -557,8 +557,10 @@ upcat_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float
     if (c < g.C1) {
       const int lz = g.S[0] > 1 ? zd >> 1 : 0;
       v = a[((((long long)n * L0 + lz) * L1 + (yh >> 1)) * L2 + (xw >> 1)) * g.C1 + c];
-    } else {
+    } else if (c < g.C1 + g.C2) {
       v = b[((((long long)n * g.S[0] + zd) * g.S[1] + yh) * g.S[2] + xw) * g.C2 + (c - g.C1)];
+    } else {
+      v = 0.f;      // channel padding (keeps the pixel stride a multiple of 16 bytes for the TMA loads of the next conv)
     }
     y[i] = v;
   }
@@ -567,7 +569,7 @@ upcat_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float
 // da = sum over the 2^nd children of dy[..., :C1];  db = dy[..., C1:]
 __global__ void __launch_bounds__(256)
 upcat_bwd_kernel(const float* __restrict__ dy, float* __restrict__ da, float* __restrict__ db, UcGeom g) {
-  const int C = g.C1 + g.C2;
+  const int C = g.Cs;
   const int L0 = g.S[0] > 1 ? g.S[0] / 2 : 1, L1 = g.S[1] / 2, L2 = g.S[2] / 2;
   const long long na = (long long)g.N * L0 * L1 * L2 * g.C1;
   const long long nb = (long long)g.N * g.S[0] * g.S[1] * g.S[2] * g.C2;
@@ -733,7 +735,7 @@ extern "C" int dfmir_blur_up_bwd(const float* dy, float* dx, int N, int H, int W
 
 static int make_uc(UcGeom& g, int N, int nd, const int* shape, int C1, int C2) {
   if ((nd != 2 && nd != 3) || N < 1 || C1 < 1 || C2 < 0) return -1;
-  g.N = N; g.nd = nd; g.C1 = C1; g.C2 = C2;
+  g.N = N; g.nd = nd; g.C1 = C1; g.C2 = C2; g.Cs = C1 + C2;
   g.S[0] = 1;
   for (int a = 0; a < nd; ++a) {
     g.S[a + 3 - nd] = shape[a];
@@ -742,25 +744,39 @@ static int make_uc(UcGeom& g, int N, int nd, const int* shape, int C1, int C2) {
   return 0;
 }
 
-extern "C" int dfmir_upsample_concat_fwd(const float* a, const float* b, float* y, int N, int nd, const int* shape,
-                                         int C1, int C2, void* stream) {
+extern "C" int dfmir_upsample_concat_padded_fwd(const float* a, const float* b, float* y, int N, int nd, const int* shape,
+                                                int C1, int C2, int Cs, void* stream) {
   UcGeom g;
   DFMIR_CHECK_ARG(make_uc(g, N, nd, shape, C1, C2) == 0, "dfmir_upsample_concat_fwd: bad geometry (even full-res dims, nd 2|3)");
   DFMIR_CHECK_ARG(a && y && (b || C2 == 0), "dfmir_upsample_concat_fwd: null pointer");
-  const long long total = (long long)N * g.S[0] * g.S[1] * g.S[2] * (C1 + C2);
+  DFMIR_CHECK_ARG(Cs >= C1 + C2, "dfmir_upsample_concat_fwd: channel stride %d smaller than %d + %d channels", Cs, C1, C2);
+  g.Cs = Cs;
+  const long long total = (long long)N * g.S[0] * g.S[1] * g.S[2] * Cs;
   upcat_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(a, b, y, g);
   DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_fwd");
   return DFMIR_OK;
 }
 
-extern "C" int dfmir_upsample_concat_bwd(const float* dy, float* da, float* db, int N, int nd, const int* shape,
-                                         int C1, int C2, void* stream) {
+extern "C" int dfmir_upsample_concat_padded_bwd(const float* dy, float* da, float* db, int N, int nd, const int* shape,
+                                                int C1, int C2, int Cs, void* stream) {
   UcGeom g;
   DFMIR_CHECK_ARG(make_uc(g, N, nd, shape, C1, C2) == 0, "dfmir_upsample_concat_bwd: bad geometry");
   DFMIR_CHECK_ARG(dy && (da || db), "dfmir_upsample_concat_bwd: null pointer");
+  DFMIR_CHECK_ARG(Cs >= C1 + C2, "dfmir_upsample_concat_bwd: channel stride %d smaller than %d + %d channels", Cs, C1, C2);
+  g.Cs = Cs;
   const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
   const long long total = (long long)N * (vox >> nd) * C1 + (long long)N * vox * C2;
   upcat_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dy, da, db, g);
   DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_bwd");
   return DFMIR_OK;
+}
+
+extern "C" int dfmir_upsample_concat_fwd(const float* a, const float* b, float* y, int N, int nd, const int* shape,
+                                         int C1, int C2, void* stream) {
+  return dfmir_upsample_concat_padded_fwd(a, b, y, N, nd, shape, C1, C2, C1 + C2, stream);
+}
+
+extern "C" int dfmir_upsample_concat_bwd(const float* dy, float* da, float* db, int N, int nd, const int* shape,
+                                         int C1, int C2, void* stream) {
+  return dfmir_upsample_concat_padded_bwd(dy, da, db, N, nd, shape, C1, C2, C1 + C2, stream);
 }

@@ -105,11 +105,12 @@ def workspace(nbytes, device):
     return buf
 
 
-def _use_umma(desc_args):
-    if CONV_ENGINE == "simt":
-        return False
+def _use_umma(d, x, y_planar, positions):
+    """Forward on the tensor cores?  (the backward products are decided one by one in _ConvFn.backward)"""
+    if CONV_ENGINE == "simt" or positions < 4096 or x.data_ptr() % 16 or d.Cin == 1 or d.Cout == 1:
+        return False      # tiny layers are launch-bound; the 7x7 stem / head have their own exact direct kernels
     from . import umma
-    return umma.supported(*desc_args)
+    return umma.supported(d, False)
 
 
 class _ConvFn(torch.autograd.Function):
@@ -135,7 +136,7 @@ class _ConvFn(torch.autograd.Function):
             bias = _f32(bias).contiguous()
         engine = "simt"
         flops = 2.0 * N * math.prod(O) * Cout * w.shape[0] * Cin
-        if _use_umma((nd, Cin, Cout, kernel, stride, pad, x, planar_out)):
+        if _use_umma(d, x, planar_out, N * math.prod(O)):
             from . import umma
             umma.conv_fwd(x, w, bias, y, d, flops)
             engine = "umma"
@@ -155,15 +156,18 @@ class _ConvFn(torch.autograd.Function):
             g = torch.empty_like(y)
             _lib.call("dfmir_act_bwd", y, dy, g, _lib.i64(y.numel()), act)
             dy = g
-        elif engine == "umma":
+        elif CONV_ENGINE != "simt" and not planar_out:
             dy = dy.contiguous()
         dx = dw = db = None
         ys = _cl_strides(dy, nd, planar_out)
+        # tensor-core engine, decided product by product (not for the stem / head: direct fp32 kernels)
+        tc = CONV_ENGINE != "simt" and N * math.prod(O) >= 4096 and Cin != 1 and Cout != 1
+        if tc:
+            from . import umma
         if ctx.needs_input_grad[0]:
             dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
-            if engine == "umma":
-                from . import umma
+            if tc and dy.data_ptr() % 16 == 0 and umma.supported(d, True):
                 umma.conv_dgrad(dy, w, dx, d, flops)
             else:
                 wt = w.transpose(1, 2).contiguous()
@@ -172,9 +176,8 @@ class _ConvFn(torch.autograd.Function):
             dw = torch.zeros_like(w)
             db = torch.zeros(Cout, dtype=w.dtype, device=w.device) if has_bias else None
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(x, nd), ys)
-            if engine == "umma":
-                from . import umma
-                umma.conv_wgrad(x, dy, dw, db, d, flops)
+            if tc and x.data_ptr() % 16 == 0 and dy.is_contiguous():
+                umma.conv_wgrad(x, dy, dw, db, d, flops)      # tcgen05 where the shape fits, else the fp32 kernel
             else:
                 _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops)
         return dx, dw, db, None, None, None, None, None
@@ -188,7 +191,10 @@ def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False):
     pads = [pad] * nd if isinstance(pad, int) else list(pad)
     Cout, Cin = weight.shape[:2]
     # (Cout,Cin,*k) -> (taps, Cin, Cout); tiny tensors, torch autograd carries the permutation back
-    w = weight.reshape(Cout, Cin, -1).permute(2, 1, 0).contiguous()
+    w = weight.reshape(Cout, Cin, -1).permute(2, 1, 0)
+    if x.shape[-1] > Cin:       # activation with zero padding channels (upsample_concat_cl(pad_channels_to=4))
+        w = torch.nn.functional.pad(w, (0, 0, 0, x.shape[-1] - Cin))
+    w = w.contiguous()
     return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out)
 
 
@@ -290,32 +296,37 @@ def blur_up_cl(x):
 
 class _UpCatFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, Cs):
         _lib.require_cuda(a, b)
         a, b = _f32(a).contiguous(), _f32(b).contiguous()
         nd = b.dim() - 2
         N, shape, C1, C2 = b.shape[0], list(b.shape[1:1 + nd]), a.shape[-1], b.shape[-1]
         if [2 * s for s in a.shape[1:1 + nd]] != shape:
             raise _lib.DfmirError(f"upsample_concat: {tuple(a.shape)} x2 does not match skip {tuple(b.shape)}")
-        y = torch.empty((N, *shape, C1 + C2), dtype=a.dtype, device=a.device)
-        _lib.call("dfmir_upsample_concat_fwd", a, b, y, N, nd, shape, C1, C2)
-        ctx.meta = (N, nd, shape, C1, C2, tuple(a.shape), tuple(b.shape))
+        y = torch.empty((N, *shape, Cs), dtype=a.dtype, device=a.device)
+        _lib.call("dfmir_upsample_concat_padded_fwd", a, b, y, N, nd, shape, C1, C2, Cs)
+        ctx.meta = (N, nd, shape, C1, C2, Cs, tuple(a.shape), tuple(b.shape))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        N, nd, shape, C1, C2, sa, sb = ctx.meta
+        N, nd, shape, C1, C2, Cs, sa, sb = ctx.meta
         dy = _f32(dy).contiguous()
         da = torch.empty(sa, dtype=dy.dtype, device=dy.device) if ctx.needs_input_grad[0] else None
         db = torch.empty(sb, dtype=dy.dtype, device=dy.device) if ctx.needs_input_grad[1] else None
         if da is not None or db is not None:
-            _lib.call("dfmir_upsample_concat_bwd", dy, da, db, N, nd, shape, C1, C2)
-        return da, db
+            _lib.call("dfmir_upsample_concat_padded_bwd", dy, da, db, N, nd, shape, C1, C2, Cs)
+        return da, db, None
 
 
-def upsample_concat_cl(a, b):
-    """cat([nearest_x2(a), b], channel) for channels-last tensors (U-Net skip connection)."""
-    return _UpCatFn.apply(a, b)
+def upsample_concat_cl(a, b, pad_channels_to=1):
+    """cat([nearest_x2(a), b], channel) for channels-last tensors (U-Net skip connection).  With
+    pad_channels_to = 4 the result carries zero channels up to a multiple of 4 (34 -> 36): the pixel stride
+    stays a multiple of 16 bytes, which the TMA loads of the tensor-core convolution need; conv_cl pads the
+    weight's input channels to match."""
+    C = a.shape[-1] + b.shape[-1]
+    Cs = (C + pad_channels_to - 1) // pad_channels_to * pad_channels_to
+    return _UpCatFn.apply(a, b, Cs)
 
 
 def _strides3(rows, cols, trans=False):

@@ -5,15 +5,14 @@ import ctypes
 
 from . import _lib
 
-_CH = (64, 128, 256)
+MIN_POSITIONS = 4096      # below this many output positions a layer is launch-bound: keep it on the fp32 kernels
 
 
-def supported(nd, Cin, Cout, kernel, stride, pad, x, planar_out):
-    """Forward AND data-gradient of this layer fit the tensor-core kernel."""
-    if nd != 2 or stride != 1 or planar_out or Cin not in _CH or Cout not in _CH:
-        return False
-    st = x.stride()
-    return st[3] == 1 and all(s % 4 == 0 for s in st[:3]) and x.data_ptr() % 16 == 0
+def supported(d, dgrad=False):
+    """This product (forward, or data gradient) of the convolution described by `d` fits the tcgen05 kernel
+    (csrc/conv_umma.cu: 2-D / 3-D, stride 1, reduction-side channels a multiple of 4 and >= 16, channels-last
+    operands with 16-byte aligned strides)."""
+    return bool(_lib.lib().dfmir_conv_umma_supported(ctypes.byref(d), int(dgrad)))
 
 
 def _run(fn, flops, kind):

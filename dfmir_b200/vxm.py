@@ -126,7 +126,7 @@ class Unet(nn.Module):
         x = x_enc.pop()
         for layer in self.uparm:
             x = layer.forward_cl(x)
-            x = Fn.upsample_concat_cl(x, x_enc.pop())
+            x = Fn.upsample_concat_cl(x, x_enc.pop(), pad_channels_to=4)
         for layer in self.extras:
             x = layer.forward_cl(x)
         return x
@@ -193,6 +193,28 @@ class VxmDense(LoadableModel):
         if not registration:
             return (y_source, y_target, pos_flow) if self.bidir else (y_source, preint_flow)
         return y_source, pos_flow
+
+    def _velocity(self, source, target):
+        """U-Net + flow head + ResizeTransform(int_downsize): the half-resolution stationary velocity field."""
+        nd = source.dim() - 2
+        x = torch.stack([source[:, 0], target[:, 0]], dim=-1) if source.shape[1] == 1 and target.shape[1] == 1 \
+            else torch.cat([source, target], dim=1).permute(0, *range(2, nd + 2), 1).contiguous()
+        x = self.unet_model.forward_cl(x)
+        flow_field = Fn.conv_cl(x, self.flow.weight, self.flow.bias, pad=1, planar_out=True)
+        return self.resize(flow_field) if self.resize else flow_field
+
+    def forward_with_losses(self, source, target, win=9, eps=1e-5, ncc="sqrt_mean", grad_penalty="l2", grad_mult=1.0):
+        """Registration forward with its two losses in ONE launch after the flow head (csrc/fused_reg.cu):
+        integrate -> fullsize resize -> warp(source) -> NCC(y_source, target) + Grad(pos_flow).
+        Returns (y_source, pos_flow, ncc_loss, grad_loss); values identical to forward() followed by
+        NCC_Loss(kernel_var=[win]*nd) / Grad_Loss(dim=nd).  Needs int_steps > 0 and int_downsize == 2."""
+        from .fused import integrate_warp_loss
+        _lib.require_cuda(source, target)
+        if self.integrate is None or self.resize is None or abs(self.resize.factor - 0.5) > 1e-12:
+            raise _lib.DfmirError("forward_with_losses: the fused launch covers int_steps > 0 with int_downsize = 2")
+        vel = self._velocity(source, target)
+        return integrate_warp_loss(vel, source, target, nsteps=self.integrate.nsteps, win=win, eps=eps, ncc=ncc,
+                                   grad_penalty=grad_penalty, grad_mult=grad_mult)
 
     def predict(self, image, flow, svf=True, **kwargs):
         if svf:

@@ -133,7 +133,8 @@ typedef struct dfmir_conv_desc {
 int dfmir_conv_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
                    void* stream);
 int dfmir_conv_dgrad(const float* dy, const float* wt, float* dx, const dfmir_conv_desc* d, void* stream);
-/* tcgen05 path (2-D, stride 1, Cin % 32 == 0, Cout in {64,128,256}; TF32 operands, fp32 accumulate in TMEM).
+/* tcgen05 path (2-D / 3-D, stride 1, reduction-side channels a multiple of 4 and >= 16, any output channel count,
+ * channels-last operands with 16-byte aligned strides; TF32 operands, fp32 accumulate in TMEM).
  * fwd weights: [tap][Cout][Cin]; dgrad weights: [tap][Cin][Cout] (each K-major for its product). */
 int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad);
 int dfmir_conv_umma_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
@@ -176,6 +177,12 @@ int dfmir_upsample_concat_fwd(const float* a, const float* b, float* y, int N, i
                               int C2, void* stream);
 int dfmir_upsample_concat_bwd(const float* dy, float* da, float* db, int N, int nd, const int* shape, int C1,
                               int C2, void* stream);
+/* same with a channel stride Cs >= C1 + C2 of y / dy (extra channels written as zero): keeps the pixel stride a
+ * multiple of 16 bytes so the next convolution can load the tensor with TMA (34 -> 36 channels in VoxelMorph) */
+int dfmir_upsample_concat_padded_fwd(const float* a, const float* b, float* y, int N, int nd, const int* shape, int C1,
+                                     int C2, int Cs, void* stream);
+int dfmir_upsample_concat_padded_bwd(const float* dy, float* da, float* db, int N, int nd, const int* shape, int C1,
+                                     int C2, int Cs, void* stream);
 
 /* ---- K6: PatchNCELoss.forward — models/patchnce.py:14-55.  q,k (B*P, D); S (B,P,P) scratch that the
  * forward leaves holding dLoss/dS; loss (B*P).  k is treated as detached (patchnce.py:17). */

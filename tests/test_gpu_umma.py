@@ -21,6 +21,10 @@ CASES = [  # N, Cin, Cout, H, W, k, pad   (H, W = input spatial size)
     (1, 128, 64, 9, 256, 3, 1),      # two tiles per row
     (3, 64, 64, 10, 10, 1, 0),       # 1x1
     (1, 256, 256, 66, 66, 3, 0),     # full-size ResnetBlock geometry: dgrad output 66x66 (partial tiles)
+    (2, 36, 16, 64, 64, 3, 1),       # VoxelMorph extras.0 on the channel-padded concat: 2 chunks (32 + 4), N tile 16
+    (2, 48, 32, 64, 64, 3, 1),       # uparm.5: partial second chunk, N tile 32
+    (2, 16, 2, 64, 64, 3, 1),        # flow head: half a chunk of K, two output channels in a 16-wide tile
+    (1, 96, 32, 64, 72, 3, 1),       # three chunks, partial tiles in w
 ]
 
 
@@ -65,12 +69,13 @@ def test_umma_conv_fwd_dgrad(case):
     finally:
         Fn.CONV_ENGINE, Fn.PROFILE = "auto", None
     wgrad_tc = bool(_wgrad_supported(Cin, Cout))
-    assert prof.umma_calls == (3 if wgrad_tc else 2), "forward, dgrad (and wgrad where covered) must run on the tensor-core engine"
+    dgrad_tc = Cout % 4 == 0 and Cout >= 16          # the data gradient reduces over Cout
+    assert prof.umma_calls == 1 + int(dgrad_tc) + int(wgrad_tc), "forward (and dgrad / wgrad where covered) must run on the tensor-core engine"
     for name, got, want, ex, em in (("fwd", tc[0], y.detach(), exact[0], emu[0]), ("dgrad", tc[1], x.grad, exact[1], emu[1]),
                                     ("wgrad", tc[2], w.grad, exact[2], emu[2])):
         scale = float(want.abs().max())
         assert float((ex - want).abs().max()) <= 2e-4 * scale, name + " (fp32 engine)"
-        if name == "wgrad" and not wgrad_tc:       # this shape's weight gradient stays on the fp32 kernel
+        if (name == "wgrad" and not wgrad_tc) or (name == "dgrad" and not dgrad_tc):   # stays on the fp32 kernel
             assert float((got - want).abs().max()) <= 2e-4 * scale
             continue
         err = float((got - want).abs().max())
@@ -86,13 +91,24 @@ def _wgrad_supported(Cin, Cout):
 
 
 def test_umma_supported_shapes():
-    import dfmir_b200.umma as umma
-    x = torch.zeros(1, 8, 8, 64, device="cuda")
-    assert umma.supported(2, 64, 128, [3, 3], 1, [1, 1], x, False)
-    assert not umma.supported(2, 1, 64, [7, 7], 1, [0, 0], x, False)       # stem
-    assert not umma.supported(2, 64, 1, [7, 7], 1, [0, 0], x, False)       # head
-    assert not umma.supported(2, 64, 128, [3, 3], 2, [1, 1], x, False)     # strided
-    assert not umma.supported(3, 64, 128, [3, 3, 3], 1, [1, 1, 1], x, False)
+    import ctypes
+    import dfmir_b200.functional as Fn
+    from dfmir_b200 import umma
+
+    def desc(nd, Cin, Cout, k, stride):
+        S = [16] * nd
+        O = [(s + 2 * (k // 2) - k) // stride + 1 for s in S]
+        xs = [int(np.prod(S)) * Cin] + [int(np.prod(S[i + 1:])) * Cin for i in range(nd)] + [1]
+        ys = [int(np.prod(O)) * Cout] + [int(np.prod(O[i + 1:])) * Cout for i in range(nd)] + [1]
+        return Fn._make_desc(nd, 1, Cin, Cout, S, O, [k] * nd, [k // 2] * nd, stride, 0, xs, ys)
+
+    assert umma.supported(desc(2, 64, 128, 3, 1)) and umma.supported(desc(2, 64, 128, 3, 1), dgrad=True)
+    assert umma.supported(desc(3, 36, 16, 3, 1)) and umma.supported(desc(3, 16, 3, 3, 1))
+    assert not umma.supported(desc(3, 16, 3, 3, 1), dgrad=True)        # reduction over 3 channels: rows not 16-byte multiples
+    assert not umma.supported(desc(2, 1, 64, 7, 1))                    # stem: one input channel
+    assert not umma.supported(desc(2, 34, 16, 3, 1))                   # 34 channels: pixel stride not a 16-byte multiple
+    assert not umma.supported(desc(2, 64, 128, 3, 2))                  # strided
+    assert not umma.supported(desc(3, 2, 16, 3, 1))                    # first encoder layer
 
 
 def test_generator_ngf64_tensor_core_vs_cpu_port():
@@ -145,3 +161,55 @@ def test_generator_ngf64_tensor_core_vs_cpu_port():
         assert e_tc <= 4.0 * e_emu + 2e-3, (k, e_tc, e_emu)
         cos = float((p.grad.cpu().double() * g64[k]).sum() / (p.grad.cpu().double().norm() * g64[k].norm()))
         assert cos >= 0.98, (k, cos)
+
+
+CASES3D = [  # N, Cin, Cout, D, H, W
+    (1, 36, 16, 16, 16, 32),         # VoxelMorph-3D extras.0 geometry (scaled down): 27 taps x 2 chunks
+    (2, 48, 32, 8, 16, 16),
+    (1, 16, 3, 12, 20, 24),          # 3-D flow head, partial tiles in every axis
+    (1, 64, 32, 16, 16, 16),
+]
+
+
+@pytest.mark.parametrize("case", CASES3D, ids=[f"v{i}" for i in range(len(CASES3D))])
+def test_umma_conv3d_fwd_dgrad(case):
+    """3-D 3x3x3 stride-1 convolutions on the tcgen05 engine (5-D TMA boxes, 27 taps): forward and data gradient
+    against the float64 CPU convolution of TF32-truncated operands (3e-5) and the exact result (3e-3); the weight
+    gradient of these shapes runs on the fp32 kernels and must be exact."""
+    from oracle import torch_port as tp
+    import dfmir_b200.functional as Fn
+    N, Cin, Cout, D, H, W = case
+    r = gi.rng(950 + Cin + Cout + D)
+    x = torch.from_numpy(r.standard_normal((N, Cin, D, H, W)).astype(np.float32)).requires_grad_()
+    w = torch.from_numpy((r.standard_normal((Cout, Cin, 3, 3, 3)) / np.sqrt(Cin * 27)).astype(np.float32)).requires_grad_()
+    b = torch.from_numpy(r.standard_normal(Cout).astype(np.float32)).requires_grad_()
+    y = F.conv3d(x, w, b, padding=1)
+    gy = torch.from_numpy(r.standard_normal(tuple(y.shape)).astype(np.float32))
+    y.backward(gy)
+    xq, wq, gq = (tp.tf32_round(t.detach()).double() for t in (x, w, gy))
+    emu_y = F.conv3d(xq, wq, b.detach().double(), padding=1)
+    emu_dx = torch.nn.grad.conv3d_input(x.shape, wq, gq, padding=1)
+    prev = Fn.CONV_ENGINE
+    Fn.CONV_ENGINE = "auto"
+    prof = Fn.ConvProfile(); Fn.PROFILE = prof
+    try:
+        xg = x.detach().cuda().permute(0, 2, 3, 4, 1).contiguous().requires_grad_()
+        wg, bg = w.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+        yg = Fn.conv_cl(xg, wg, bg, pad=1)
+        yg.backward(gy.cuda().permute(0, 2, 3, 4, 1).contiguous())
+        torch.cuda.synchronize()
+    finally:
+        Fn.CONV_ENGINE, Fn.PROFILE = prev, None
+    kinds = prof.by_kind()
+    assert "umma_fwd" in kinds, kinds.keys()
+    if Cout % 4 == 0 and Cout >= 16:
+        assert "umma_dgrad" in kinds, kinds.keys()
+    got_y = yg.detach().permute(0, 4, 1, 2, 3).cpu()
+    got_dx = xg.grad.permute(0, 4, 1, 2, 3).cpu()
+    for name, got, want, em in (("fwd", got_y, y.detach(), emu_y), ("dgrad", got_dx, x.grad, emu_dx)):
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 3e-3 * scale, name
+        if name == "fwd" or "umma_dgrad" in kinds:
+            assert float((got.double() - em).abs().max()) <= 3e-5 * scale, (name, "vs TF32-truncated float64 reference")
+    np.testing.assert_allclose(wg.grad.cpu().numpy(), w.grad.numpy(), atol=2e-4 * float(w.grad.abs().max()))
+    np.testing.assert_allclose(bg.grad.cpu().numpy(), b.grad.numpy(), atol=2e-4 * float(b.grad.abs().max()))
