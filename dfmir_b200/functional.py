@@ -17,6 +17,9 @@ ACT_NONE, ACT_LEAKY, ACT_TANH, ACT_RELU = 0, 1, 2, 3
 # convolution engine: "simt" = fp32 CUDA cores (exact), "umma" = tcgen05 tensor cores (TF32 operands)
 # for the layer shapes it supports, "auto" = umma where supported.
 CONV_ENGINE = os.environ.get("DFMIR_CONV_ENGINE", "auto")
+# layers with fewer output positions than this stay on the fp32 kernels (launch-bound; TMA descriptor set-up
+# would dominate).  Tests set it to 0 to drive small shapes through the tensor-core kernels.
+UMMA_MIN_POSITIONS = int(os.environ.get("DFMIR_UMMA_MIN_POSITIONS", "4096"))
 
 
 class ConvProfile:
@@ -107,7 +110,7 @@ def workspace(nbytes, device):
 
 def _use_umma(d, x, y_planar, positions):
     """Forward on the tensor cores?  (the backward products are decided one by one in _ConvFn.backward)"""
-    if CONV_ENGINE == "simt" or positions < 4096 or x.data_ptr() % 16 or d.Cin == 1 or d.Cout == 1:
+    if CONV_ENGINE == "simt" or positions < UMMA_MIN_POSITIONS or x.data_ptr() % 16 or d.Cin == 1 or d.Cout == 1:
         return False      # tiny layers are launch-bound; the 7x7 stem / head have their own exact direct kernels
     from . import umma
     return umma.supported(d, False)
@@ -161,7 +164,7 @@ class _ConvFn(torch.autograd.Function):
         dx = dw = db = None
         ys = _cl_strides(dy, nd, planar_out)
         # tensor-core engine, decided product by product (not for the stem / head: direct fp32 kernels)
-        tc = CONV_ENGINE != "simt" and N * math.prod(O) >= 4096 and Cin != 1 and Cout != 1
+        tc = CONV_ENGINE != "simt" and N * math.prod(O) >= UMMA_MIN_POSITIONS and Cin != 1 and Cout != 1
         if tc:
             from . import umma
         if ctx.needs_input_grad[0]:

@@ -13,6 +13,16 @@ import inputs as gi
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def small_shapes_on_tensor_cores():
+    """The engine keeps layers with < 4096 output positions on the fp32 kernels; the unit shapes here are smaller."""
+    import dfmir_b200.functional as Fn
+    prev = Fn.UMMA_MIN_POSITIONS
+    Fn.UMMA_MIN_POSITIONS = 0
+    yield
+    Fn.UMMA_MIN_POSITIONS = prev
+
 CASES = [  # N, Cin, Cout, H, W, k, pad   (H, W = input spatial size)
     (2, 64, 128, 16, 128, 3, 1),     # TW = 128, TH = 1
     (2, 128, 256, 8, 64, 3, 1),      # TW = 64, TH = 2
