@@ -249,6 +249,192 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
+// ---------------------------------------------------------------- halo variant
+// Same product, different operand delivery: per 32-channel chunk ONE activation tile WITH ITS HALO is
+// loaded (box {32, 8*SW+KW-1, 16*SH+KH-1, SD+KD-1, 1}, rows in (d,h,w) order), and every tap reads its
+// shifted window of that tile through the UMMA descriptor: start address = the window's first row, stride
+// between 8-row groups = the halo row pitch.  SWIZZLE_128B is a function of the absolute shared-memory
+// address, so a window may start at any 128-byte row and use any 128-byte-multiple group stride (measured:
+// tools/umma_shift_probe.cu).  A sub-tile is 16 (h) x 8 (w) voxels at one depth: its sixteen 8-row groups
+// are exactly (8*SW+KW-1) rows apart.  Activation traffic per output voxel drops from taps x 128 B to
+// ~1.3-2 x 128 B per chunk (9x / 27x fewer L2 -> shared-memory bytes in 2-D / 3-D); the weights stream as
+// before, one {32, BN} box per (tap, chunk) through their own deeper pipeline.
+template <int BN, int SD, int SH, int SW, int BST>
+struct HaloCfg {
+  static constexpr int MT = SD * SH * SW;
+  static constexpr int AS = (2 * MT * BN <= 512) ? 2 : 1;
+  static constexpr int B_BYTES = BN * 128;
+};
+
+struct HaloP {
+  UmmaP u;
+  int HD, HH, HW;          // halo tile extents
+  int a_bytes;             // bytes of one activation stage (rows * 128, rounded up to 1024)
+};
+
+template <int BN, int SD, int SH, int SW, int BST>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const float* __restrict__ bias, float* __restrict__ y, const HaloP hp) {
+  using C = HaloCfg<BN, SD, SH, SW, BST>;
+  constexpr int MT = C::MT, AS = C::AS;
+  constexpr int CW = BN < 32 ? BN : 32;
+  const UmmaP& p = hp.u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                              // 2 activation stages
+  uint8_t* sB = smem + 2 * hp.a_bytes;             // BST weight stages
+  uint64_t* a_full = (uint64_t*)(sB + BST * C::B_BYTES);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + BST;
+  uint64_t* tmem_full = b_empty + BST;
+  uint64_t* tmem_empty = tmem_full + AS;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + AS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int tiles_hw = p.tiles_h * p.tiles_w;
+  const int tiles_per_img = p.tiles_d * tiles_hw;
+  const int items = p.ptiles * n_tiles;            // ptiles = CTA tiles here (each MT sub-tiles)
+  const int cchunks = (p.Cin + KCH - 1) / KCH;
+  const int taps = p.KD * p.KH * p.KW;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < BST; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int a = 0; a < AS; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      uint32_t ia = 0, ib = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int nt = item % n_tiles, pt = item / n_tiles;
+        const int n = pt / tiles_per_img; int rem = pt - n * tiles_per_img;
+        const int td_i = rem / tiles_hw; rem -= td_i * tiles_hw;
+        const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        const int d0 = td_i * SD, h0 = th_i * 16 * SH, w0 = tw_i * 8 * SW;
+        for (int cc = 0; cc < cchunks; ++cc, ++ia) {
+          const int sa = ia & 1;
+          mbar_wait(a_empty + sa, ((ia >> 1) & 1) ^ 1);
+          mbar_expect_tx(a_full + sa, (uint32_t)(hp.HD * hp.HH * hp.HW * 128));
+          tma_load_5d(sA + sa * hp.a_bytes, &tmA, a_full + sa, cc * KCH, w0 - p.pad_w, h0 - p.pad_h, d0 - p.pad_d, n);
+          for (int tap = 0; tap < taps; ++tap, ++ib) {
+            const int sb = ib % BST;
+            mbar_wait(b_empty + sb, ((ib / BST) & 1) ^ 1);
+            mbar_expect_tx(b_full + sb, (uint32_t)C::B_BYTES);
+            tma_load_3d(sB + sb * C::B_BYTES, &tmB, b_full + sb, cc * KCH, nt * BN, p.flip ? taps - 1 - tap : tap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
+      const uint32_t sbo = (uint32_t)hp.HW * 128u;             // next h row of the halo tile
+      uint32_t ia = 0, ib = 0, ti = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+        const uint32_t as = ti % AS, aph = (ti / AS) & 1;
+        mbar_wait(tmem_empty + as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * (MT * BN);
+        for (int cc = 0; cc < cchunks; ++cc, ++ia) {
+          const int sa = ia & 1;
+          mbar_wait(a_full + sa, (ia >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + sa * hp.a_bytes);
+          int tap = 0;
+          for (int kd = 0; kd < p.KD; ++kd)
+            for (int r = 0; r < p.KH; ++r)
+              for (int q = 0; q < p.KW; ++q, ++tap, ++ib) {
+                const int sb = ib % BST;
+                mbar_wait(b_full + sb, (ib / BST) & 1);
+                tc_fence_after();
+                const uint64_t bdesc = smem_desc_sw128(smem_u32(sB + sb * C::B_BYTES), 16, 1024);
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                  const int sw = j % SW, sh = (j / SW) % SH, sd = j / (SW * SH);
+                  const uint32_t row = (uint32_t)(((sd + kd) * hp.HH + 16 * sh + r) * hp.HW + 8 * sw + q);
+                  const uint64_t adesc = smem_desc_sw128(a_base + row * 128u, 16, sbo);
+#pragma unroll
+                  for (int k = 0; k < KCH / UMMA_K; ++k)
+                    umma_tf32(acc + j * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (cc | tap | k) != 0);
+                }
+                umma_commit(b_empty + sb);
+              }
+          umma_commit(a_empty + sa);           // every tap of this chunk has been issued: frees the halo tile when they retire
+        }
+        umma_commit(tmem_full + as);
+      }
+    }
+  } else {
+    // ---------------- epilogue
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    const int jfirst = e >> 2;
+    const int row = quarter * 32 + lane;
+    const int th = row >> 3, tw = row & 7;
+    const bool vec_ok = p.ys[4] == 1 && (p.Cout & 3) == 0;
+    uint32_t ti = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
+      const uint32_t as = ti % AS, aph = (ti / AS) & 1;
+      const int nt = item % n_tiles, pt = item / n_tiles;
+      const int n0 = nt * BN;
+      const int n = pt / tiles_per_img; int rem = pt - n * tiles_per_img;
+      const int td_i = rem / tiles_hw; rem -= td_i * tiles_hw;
+      const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+      mbar_wait(tmem_full + as, aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = jfirst; j < MT; j += EPI_WARPS / 4) {
+        const int sw = j % SW, sh = (j / SW) % SH, sd = j / (SW * SH);
+        const int od = td_i * SD + sd, oh = th_i * 16 * SH + 16 * sh + th, ow = tw_i * 8 * SW + 8 * sw + tw;
+        const bool valid = od < p.D && oh < p.H && ow < p.W;
+        float* yp = y + (long long)n * p.ys[0] + (long long)od * p.ys[1] + (long long)oh * p.ys[2] + (long long)ow * p.ys[3];
+        const uint32_t acc = tmem_base + as * (MT * BN) + j * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CW) {
+          float v[CW];
+          if (CW == 32) tmem_ld_32x32(acc + (uint32_t)c0, v); else tmem_ld_32x16(acc + (uint32_t)c0, v);
+          if (valid && n0 + c0 < p.Cout) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+              float t = v[i];
+              if (bias && n0 + c0 + i < p.Cout) t += __ldg(bias + n0 + c0 + i);
+              v[i] = act_apply(t, p.act);
+            }
+            if (vec_ok && n0 + c0 + CW <= p.Cout) {
+              float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
+#pragma unroll
+              for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < CW; ++i)
+                if (n0 + c0 + i < p.Cout) yp[(long long)(n0 + c0 + i) * p.ys[4]] = v[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 // ---------------------------------------------------------------- host side
 // strides arrive as {n, spatial[nd], c}
 struct Strides5 { long long n, d, h, w, c; };
@@ -336,6 +522,41 @@ int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
   return DFMIR_OK;
 }
 
+template <int BN, int SD, int SH, int SW, int BST>
+int launch_halo(const float* act, const Strides5& as, int ID, int IH, int IW, const CUtensorMap& tmB, const float* bias, float* y,
+                UmmaP p, cudaStream_t st, const char* who) {
+  using C = HaloCfg<BN, SD, SH, SW, BST>;
+  HaloP hp;
+  hp.HD = SD + p.KD - 1; hp.HH = 16 * SH + p.KH - 1; hp.HW = 8 * SW + p.KW - 1;
+  hp.a_bytes = (hp.HD * hp.HH * hp.HW * 128 + 1023) / 1024 * 1024;
+  const int nbars = 4 + 2 * BST + 2 * C::AS;
+  const size_t smem = 2 * (size_t)hp.a_bytes + (size_t)BST * C::B_BYTES + nbars * 8 + 16 + 1024;
+  if (smem > 227 * 1024 || hp.HW > 256 || hp.HH > 256 || hp.HD > 256) return DFMIR_ERR_UNSUPPORTED;
+  p.tiles_d = (p.D + SD - 1) / SD; p.tiles_h = (p.H + 16 * SH - 1) / (16 * SH); p.tiles_w = (p.W + 8 * SW - 1) / (8 * SW);
+  p.ptiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w;
+  hp.u = p;
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  CUtensorMap tmA;
+  const long long sd = ID > 1 ? as.d : as.h * IH;
+  cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)ID, (cuuint64_t)p.N};
+  cuuint64_t strides[4] = {(cuuint64_t)as.w * 4, (cuuint64_t)as.h * 4, (cuuint64_t)sd * 4, (cuuint64_t)as.n * 4};
+  cuuint32_t box[5] = {KCH, (cuuint32_t)hp.HW, (cuuint32_t)hp.HH, (cuuint32_t)hp.HD, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(halo tile) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<BN, SD, SH, SW, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int items = p.ptiles * ((p.Cout + BN - 1) / BN);
+  if (items == 0) return DFMIR_OK;
+  int grid = dfmir_num_sms();
+  if (grid > items) grid = items;
+  const int rounds = (items + grid - 1) / grid;
+  grid = (items + rounds - 1) / rounds;
+  conv_umma_halo_kernel<BN, SD, SH, SW, BST><<<grid, THREADS, smem, st>>>(tmA, tmB, bias, y, hp);
+  DFMIR_CHECK_LAUNCH(who);
+  return DFMIR_OK;
+}
+
 // act: source activation (channels-last, c stride 1) with element strides `as` and spatial size (ID, IH, IW)
 int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const float* w, const float* bias, float* y,
              const UmmaP& p, cudaStream_t st, const char* who) {
@@ -365,6 +586,23 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  }
+  // halo variant (one activation tile per chunk serves every tap): kernels larger than 1x1
+  static const int halo = getenv("DFMIR_UMMA_HALO") ? atoi(getenv("DFMIR_UMMA_HALO")) : 1;
+  if (halo && p.KD * p.KH * p.KW > 1 && BN <= 128) {
+    int rc = DFMIR_ERR_UNSUPPORTED;
+    if (ID > 1) {
+      if (BN == 128) rc = launch_halo<128, 2, 1, 1, 2>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      else if (BN == 64) rc = launch_halo<64, 2, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      else if (BN == 32) rc = launch_halo<32, 2, 1, 1, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      else rc = launch_halo<16, 2, 1, 1, 8>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+    } else {
+      if (BN == 128) rc = launch_halo<128, 1, 1, 2, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      else if (BN == 64) rc = launch_halo<64, 1, 2, 2, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      else if (BN == 32) rc = launch_halo<32, 1, 2, 2, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      else rc = launch_halo<16, 1, 2, 2, 8>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+    }
+    if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
   }
   // 128-channel tiles x 2 sub-tiles: 48 KB stages x 4 and double-buffered accumulators beat one 256-wide tile
   // (64 KB x 3, no epilogue overlap): 552 vs 430 TFLOP/s on the ResnetBlock conv at batch 32

