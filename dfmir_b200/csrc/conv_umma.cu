@@ -565,7 +565,13 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
   if (((uintptr_t)act & 15) || ((uintptr_t)w & 15)) { dfmir_set_error("%s: TMA needs 16-byte aligned base pointers", who); return DFMIR_ERR_ARG; }
   int BN = p.Cout <= 16 ? 16 : (p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : 128));
-  if (p.Cout == 256 && (cfg == 1 || cfg == 5)) BN = 256;
+  if (p.Cout == 256 && (cfg == 1 || cfg == 5 || cfg == 6 || cfg == 7)) BN = 256;
+  // 16x16-voxel CTA tiles waste a third of the work on a 66x66 output (the data gradient of the ResnetBlock
+  // convs): there, 16x8 tiles with all 256 channels per CTA measured 542 vs 441 TFLOP/s (batch 32)
+  const double eff16 = (double)p.H * p.W / ((double)((p.H + 15) / 16 * 16) * ((p.W + 15) / 16 * 16));
+  const double eff8 = (double)p.H * p.W / ((double)((p.H + 15) / 16 * 16) * ((p.W + 7) / 8 * 8));
+  const bool narrow256 = p.Cout == 256 && ID == 1 && p.KD * p.KH * p.KW > 1 && eff16 < 0.72 && eff8 > eff16 * 1.08 && cfg == 0;
+  if (narrow256) BN = 256;
   CUtensorMap tmA, tmB;
   {
     const long long sd = ID > 1 ? as.d : as.h * IH;      // 2-D: a depth axis of extent 1 (its stride is never used)
@@ -589,6 +595,16 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   }
   // halo variant (one activation tile per chunk serves every tap): kernels larger than 1x1
   static const int halo = getenv("DFMIR_UMMA_HALO") ? atoi(getenv("DFMIR_UMMA_HALO")) : 1;
+  if (halo && narrow256) {
+    int rc = launch_halo<256, 1, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+    if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
+  }
+  if (halo && p.KD * p.KH * p.KW > 1 && BN == 256 && ID == 1 && (cfg == 6 || cfg == 7)) {
+    // experiment: 256-wide tiles (operand reads 96 B/clk instead of 128) on the halo pipeline, no epilogue overlap
+    int rc = cfg == 6 ? launch_halo<256, 1, 1, 2, 3>(act, as, ID, IH, IW, tmB, bias, y, p, st, who)
+                      : launch_halo<256, 1, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+    if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
+  }
   if (halo && p.KD * p.KH * p.KW > 1 && BN <= 128) {
     int rc = DFMIR_ERR_UNSUPPORTED;
     if (ID > 1) {

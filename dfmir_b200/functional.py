@@ -380,6 +380,14 @@ class _LinearFn(torch.autograd.Function):
 
 
 def linear(x, W, b, relu=False):
+    """y = relu?(x W^T + b).  On the tensor-core engine a row-major (M, K) x (N, K)^T product IS a 1x1 convolution
+    over M pixels with K input and N output channels: large ones (the PatchSampleF MLP at 4096+ rows) run on
+    conv_umma_kernel (forward, dx and dW), the rest on the fp32 GEMM kernel."""
+    M, K = x.shape
+    if (CONV_ENGINE != "simt" and M >= UMMA_MIN_POSITIONS and M % 64 == 0 and K % 4 == 0 and K >= 16
+            and x.is_contiguous() and x.data_ptr() % 16 == 0):
+        y = conv_cl(x.view(1, M // 64, 64, K), W.view(W.shape[0], K, 1, 1), b, act=ACT_RELU if relu else ACT_NONE)
+        return y.view(M, W.shape[0])
     return _LinearFn.apply(x, W, b, relu)
 
 
