@@ -11,7 +11,9 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 19
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.dfmir_abi_version() == 2
+    import re
+    want = int(re.search(r"#define DFMIR_ABI_VERSION (\d+)", open(_lib.HEADER_PATH).read()).group(1))
+    assert lib.dfmir_abi_version() == want
 
 
 def test_no_cpu_fallback():
