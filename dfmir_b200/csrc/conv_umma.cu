@@ -50,6 +50,7 @@ struct UmmaP {
   int ptiles;             // N * tiles_d * tiles_h * tiles_w sub-tiles of 128 voxels
   int flip;               // 1: use tap (taps-1-t) of the weight tensor (data gradient)
   int act;
+  int per_sample;         // 1: the "tap" coordinate of the weight map is the sample index (batched A[b] * B[b]^T)
   long long ys[5];        // output element strides n, d, h, w, c
 };
 
@@ -155,7 +156,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < MT; ++j)
             tma_load_5d(sa + j * A_BYTES, &tmA, full + s, cc * KCH, sw[j] + q - p.pad_w, sh[j] + r - p.pad_h,
                         sd[j] + kd - p.pad_d, sn[j]);
-          tma_load_3d(sa + MT * A_BYTES, &tmB, full + s, cc * KCH, nt * BN, p.flip ? taps - 1 - tap : tap);
+          tma_load_3d(sa + MT * A_BYTES, &tmB, full + s, cc * KCH, nt * BN,
+                      p.per_sample ? sn[0] : (p.flip ? taps - 1 - tap : tap));
         }
       }
     }
@@ -483,7 +485,7 @@ int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
   }
   p.KD = K[0]; p.KH = K[1]; p.KW = K[2]; p.pad_d = P[0]; p.pad_h = P[1]; p.pad_w = P[2];
   p.D = O[0]; p.H = O[1]; p.W = O[2];
-  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act;
+  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act; p.per_sample = 0;
   const Strides5 os = spread(dgrad ? d->x_strides : d->y_strides, nd);
   p.ys[0] = os.n; p.ys[1] = os.d; p.ys[2] = os.h; p.ys[3] = os.w; p.ys[4] = os.c;
   // tile box TD x TH x TW = 128 voxels (powers of two, TW >= 8): the shape that wastes the fewest voxels on
@@ -565,7 +567,7 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
   if (((uintptr_t)act & 15) || ((uintptr_t)w & 15)) { dfmir_set_error("%s: TMA needs 16-byte aligned base pointers", who); return DFMIR_ERR_ARG; }
   int BN = p.Cout <= 16 ? 16 : (p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : 128));
-  if (p.Cout == 256 && (cfg == 1 || cfg == 5 || cfg == 6 || cfg == 7)) BN = 256;
+  if (p.Cout == 256 && (cfg == 1 || cfg == 5 || cfg == 6 || cfg == 7 || cfg == 8)) BN = 256;
   // 16x16-voxel CTA tiles waste a third of the work on a 66x66 output (the data gradient of the ResnetBlock
   // convs): there, 16x8 tiles with all 256 channels per CTA measured 542 vs 441 TFLOP/s (batch 32)
   const double eff16 = (double)p.H * p.W / ((double)((p.H + 15) / 16 * 16) * ((p.W + 15) / 16 * 16));
@@ -584,7 +586,7 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
     if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(activation) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
   }
   {
-    const int taps = p.KD * p.KH * p.KW;
+    const int taps = p.per_sample ? p.N : p.KD * p.KH * p.KW;
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
     cuuint32_t box[3] = {KCH, (cuuint32_t)BN, 1};
@@ -597,6 +599,10 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   static const int halo = getenv("DFMIR_UMMA_HALO") ? atoi(getenv("DFMIR_UMMA_HALO")) : 1;
   if (halo && narrow256) {
     int rc = launch_halo<256, 1, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+    if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
+  }
+  if (halo && p.KD * p.KH * p.KW > 1 && BN == 256 && ID == 1 && cfg == 8) {
+    int rc = launch_halo<256, 1, 1, 2, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
     if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
   }
   if (halo && p.KD * p.KH * p.KW > 1 && BN == 256 && ID == 1 && (cfg == 6 || cfg == 7)) {
@@ -660,4 +666,52 @@ extern "C" int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx,
   const int nd = d->nd;
   return run_umma(dy, spread(d->y_strides, nd), nd == 3 ? d->out_shape[0] : 1, d->out_shape[nd - 2], d->out_shape[nd - 1], w, nullptr,
                   dx, p, (cudaStream_t)stream, "dfmir_conv_umma_dgrad");
+}
+
+// Batched C[b] (M x N) = A[b] (M x K) * B[b]^T (N x K), all row-major and dense, on the same tcgen05 kernel:
+// the M rows of a sample are the "pixels", K the input channels, and the weight map's tap coordinate selects
+// the sample.  Used for the PatchNCE logits S = Q K^T (models/patchnce.py:20,42) and their backward product.
+// TF32 operands: callers that need fp32-class accuracy pass the 3-way split operands of dfmir_tf32_split3.
+extern "C" int dfmir_bmm_nt_umma(const float* A, const float* B, float* C, int batch, int M, int N, int K, void* stream) {
+  const char* who = "dfmir_bmm_nt_umma";
+  DFMIR_CHECK_ARG(A && B && C, "%s: null pointer", who);
+  DFMIR_CHECK_ARG(batch >= 1 && M >= 128 && M % 128 == 0 && N >= 1 && K >= 16 && K % 4 == 0,
+                  "%s: needs M %% 128 == 0, K %% 4 == 0, K >= 16 (got batch=%d M=%d N=%d K=%d)", who, batch, M, N, K);
+  UmmaP p{};
+  p.N = batch; p.D = 1; p.H = 1; p.W = M; p.Cin = K; p.Cout = N;
+  p.KD = p.KH = p.KW = 1; p.pad_d = p.pad_h = p.pad_w = 0;
+  p.TD = 1; p.TH = 1; p.TW = 128; p.tiles_d = 1; p.tiles_h = 1; p.tiles_w = M / 128;
+  p.ptiles = batch * p.tiles_w; p.flip = 0; p.act = DFMIR_ACT_NONE; p.per_sample = 1;
+  p.ys[0] = (long long)M * N; p.ys[1] = 0; p.ys[2] = 0; p.ys[3] = N; p.ys[4] = 1;
+  const int mt = N <= 64 ? 4 : 2;      // sub-tiles per work item of the tile configuration run_umma picks
+  DFMIR_CHECK_ARG(p.tiles_w % mt == 0, "%s: M = %d must be a multiple of %d so that a work item stays inside one sample", who, M, 128 * mt);
+  Strides5 as; as.n = (long long)M * K; as.d = 0; as.h = (long long)M * K; as.w = K; as.c = 1;
+  return run_umma(A, as, 1, 1, M, B, nullptr, C, p, (cudaStream_t)stream, who);
+}
+
+namespace {
+// out (rows, 3*D): a-style [hi | hi | lo], b-style [hi | lo | hi]; hi = x truncated to TF32 (what the tensor core
+// keeps), lo = x - hi (exact).  sum over the 3D columns of a-style * b-style = hi*hi + hi*lo + lo*hi.
+__global__ void __launch_bounds__(256)
+tf32_split3_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, int D, int b_style) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D; const int c = (int)(i - r * D);
+    const float v = x[i];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const float lo = v - hi;
+    float* o = out + r * 3 * D + c;
+    o[0] = hi; o[D] = b_style ? lo : hi; o[2 * D] = b_style ? hi : lo;
+  }
+}
+}  // namespace
+
+extern "C" int dfmir_tf32_split3(const float* x, float* out, long long rows, int D, int b_style, void* stream) {
+  DFMIR_CHECK_ARG(x && out && rows >= 0 && D > 0, "dfmir_tf32_split3: bad argument");
+  const long long total = rows * D;
+  if (total == 0) return DFMIR_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)dfmir_num_sms() * 16;
+  tf32_split3_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(x, out, total, D, b_style);
+  DFMIR_CHECK_LAUNCH("dfmir_tf32_split3");
+  return DFMIR_OK;
 }

@@ -305,3 +305,31 @@ extern "C" int dfmir_gather_patches_bwd(const float* dout, const long long* ids,
   DFMIR_CHECK_LAUNCH("dfmir_gather_patches_bwd");
   return DFMIR_OK;
 }
+
+// ---- tensor-core variant of the two PatchNCE products (conv_umma.cu: dfmir_bmm_nt_umma on 3xTF32-split operands)
+extern "C" int dfmir_bmm_nt_umma(const float* A, const float* B, float* C, int batch, int M, int N, int K, void* stream);
+
+// q3 (B*P, 3D) a-style split of q, k3 (B*P, 3D) b-style split of k (dfmir_tf32_split3) -> S, loss as dfmir_patchnce_fwd
+extern "C" int dfmir_patchnce_tc_fwd(const float* q3, const float* k3, float* S, float* loss, int B, int P, int D3, float T,
+                                     void* stream) {
+  DFMIR_CHECK_ARG(q3 && k3 && S && loss, "dfmir_patchnce_tc_fwd: null pointer");
+  DFMIR_CHECK_ARG(B > 0 && P > 0 && D3 > 0 && T > 0.f, "dfmir_patchnce_tc_fwd: bad sizes");
+  int rc = dfmir_bmm_nt_umma(q3, k3, S, B, P, P, D3, stream);
+  if (rc) return rc;
+  const int rows = B * P;
+  patchnce_rows_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(S, loss, rows, P, 1.0f / T);
+  DFMIR_CHECK_LAUNCH("dfmir_patchnce_tc_fwd(rows)");
+  return DFMIR_OK;
+}
+
+// work[row][:] = S[row][:] * g[row]  (first half of dfmir_patchnce_bwd; the product dq = work * k then runs on the
+// tensor-core kernel as dfmir_bmm_nt_umma(work3, kT3))
+extern "C" int dfmir_patchnce_scale(const float* S, const float* g, float* work, int B, int P, void* stream) {
+  DFMIR_CHECK_ARG(S && g && work && B > 0 && P > 0, "dfmir_patchnce_scale: bad argument");
+  const long long rows = (long long)B * P;
+  long long blocks = (rows * P + 255) / 256;
+  const long long cap = (long long)dfmir_num_sms() * 16;
+  row_scale_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(S, g, work, rows, P);
+  DFMIR_CHECK_LAUNCH("dfmir_patchnce_scale");
+  return DFMIR_OK;
+}

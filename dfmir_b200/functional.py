@@ -450,7 +450,18 @@ def gather_patches(feat, ids):
     return _GatherFn.apply(feat, ids)
 
 
+def _split3(x, b_style):
+    rows, D = x.shape
+    out = torch.empty((rows, 3 * D), dtype=x.dtype, device=x.device)
+    _lib.call("dfmir_tf32_split3", x, out, _lib.i64(rows), D, int(b_style))
+    return out
+
+
 class _PatchNCEFn(torch.autograd.Function):
+    """PatchNCELoss.forward.  Tensor-core engine: S = Q K^T and dQ = dS K run on conv_umma_kernel as batched
+    products of 3xTF32-split operands (hi*hi + hi*lo + lo*hi, fp32-class accuracy like the reference's fp32
+    torch.bmm); fp32 engine: the CUDA-core GEMM."""
+
     @staticmethod
     def forward(ctx, q, k, B, T):
         _lib.require_cuda(q, k)
@@ -461,19 +472,28 @@ class _PatchNCEFn(torch.autograd.Function):
         P = rows // B
         S = torch.empty((B, P, P), dtype=q.dtype, device=q.device)
         loss = torch.empty(rows, dtype=q.dtype, device=q.device)
-        _lib.call("dfmir_patchnce_fwd", q, k, S, loss, B, P, D, float(T))
+        tc = CONV_ENGINE != "simt" and P % 256 == 0 and D % 4 == 0 and D >= 16
+        if tc:
+            _lib.call("dfmir_patchnce_tc_fwd", _split3(q, False), _split3(k, True), S, loss, B, P, 3 * D, float(T))
+        else:
+            _lib.call("dfmir_patchnce_fwd", q, k, S, loss, B, P, D, float(T))
         ctx.save_for_backward(S, k)
-        ctx.meta = (B, P, D)
+        ctx.meta = (B, P, D, tc)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         S, k = ctx.saved_tensors
-        B, P, D = ctx.meta
+        B, P, D, tc = ctx.meta
         g = _f32(g).contiguous()
         work = torch.empty_like(S)
         dq = torch.empty((B * P, D), dtype=g.dtype, device=g.device)
-        _lib.call("dfmir_patchnce_bwd", S, k, g, work, dq, B, P, D)
+        if tc and D % 128 == 0:
+            _lib.call("dfmir_patchnce_scale", S, g, work, B, P)
+            kT = k.view(B, P, D).transpose(1, 2).contiguous().view(B * D, P)       # B[b]^T rows = feature dims
+            _lib.call("dfmir_bmm_nt_umma", _split3(work.view(B * P, P), False), _split3(kT, True), dq, B, P, D, 3 * P)
+        else:
+            _lib.call("dfmir_patchnce_bwd", S, k, g, work, dq, B, P, D)
         return dq, None, None, None
 
 

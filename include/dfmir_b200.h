@@ -190,6 +190,15 @@ int dfmir_patchnce_fwd(const float* q, const float* k, float* S, float* loss, in
                        void* stream);
 int dfmir_patchnce_bwd(const float* S, const float* k, const float* g, float* work, float* dq, int B, int P, int D,
                        void* stream);
+/* tensor-core variant (K6): the two products run on the tcgen05 kernel through dfmir_bmm_nt_umma with 3xTF32-split
+ * operands (hi*hi + hi*lo + lo*hi: fp32-class accuracy, the reference's torch.bmm is fp32).
+ * dfmir_tf32_split3: x (rows, D) -> out (rows, 3D), a-style [hi|hi|lo] or b-style [hi|lo|hi].
+ * dfmir_bmm_nt_umma: C[b] (M,N) = A[b] (M,K) * B[b]^T (N,K), dense row-major, M % 256 == 0 (N > 64), K % 4 == 0. */
+int dfmir_tf32_split3(const float* x, float* out, long long rows, int D, int b_style, void* stream);
+int dfmir_bmm_nt_umma(const float* A, const float* B, float* C, int batch, int M, int N, int K, void* stream);
+int dfmir_patchnce_tc_fwd(const float* q3, const float* k3, float* S, float* loss, int B, int P, int D3, float T,
+                          void* stream);
+int dfmir_patchnce_scale(const float* S, const float* g, float* work, int B, int P, void* stream);
 /* ---- PatchSampleF — models/networks.py:597-624: patch gather, MLP products, L2 normalisation */
 int dfmir_gather_patches_fwd(const float* feat, const long long* ids, float* out, int B, int P, int C, int Wd,
                              const long long* strides, void* stream);

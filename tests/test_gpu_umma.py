@@ -223,3 +223,34 @@ def test_umma_conv3d_fwd_dgrad(case):
             assert float((got.double() - em).abs().max()) <= 3e-5 * scale, (name, "vs TF32-truncated float64 reference")
     np.testing.assert_allclose(wg.grad.cpu().numpy(), w.grad.numpy(), atol=2e-4 * float(w.grad.abs().max()))
     np.testing.assert_allclose(bg.grad.cpu().numpy(), b.grad.numpy(), atol=2e-4 * float(b.grad.abs().max()))
+
+
+def test_patchnce_tensor_core_3xtf32(orc):
+    """K6: PatchNCE logits S = Q K^T and dQ = dS K on the tcgen05 kernel (batched, per-sample weight tiles) with
+    3xTF32-split operands: must agree with the fp32 CUDA-core path and the C oracle to fp32 accuracy (the reference's
+    torch.bmm is fp32), far tighter than plain TF32 would (1e-3 * logits / T)."""
+    import dfmir_b200.functional as Fn
+    B, P, D = 3, 256, 256
+    r = gi.rng(77)
+    q = r.standard_normal((B * P, D)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    k = r.standard_normal((B * P, D)).astype(np.float32); k /= np.linalg.norm(k, axis=1, keepdims=True)
+    k = (0.6 * q + 0.4 * k).astype(np.float32)            # correlated positives
+    gw = r.standard_normal(B * P).astype(np.float32)
+    res = {}
+    for eng in ("simt", "auto"):
+        Fn.CONV_ENGINE = eng
+        try:
+            qg = torch.from_numpy(q).cuda().requires_grad_()
+            n0 = None
+            loss = Fn.patchnce(qg, torch.from_numpy(k).cuda(), B, 0.07)
+            (loss * torch.from_numpy(gw).cuda()).sum().backward()
+            res[eng] = (loss.detach().cpu().numpy(), qg.grad.cpu().numpy())
+        finally:
+            Fn.CONV_ENGINE = "auto"
+    want = orc.patchnce(q, k, B, 0.07)
+    np.testing.assert_allclose(res["simt"][0], want, atol=1e-4)
+    np.testing.assert_allclose(res["auto"][0], want, atol=1e-4)
+    np.testing.assert_allclose(res["auto"][0], res["simt"][0], atol=2e-5)
+    np.testing.assert_allclose(res["auto"][1], res["simt"][1], atol=2e-5 * np.abs(res["simt"][1]).max())
+    # the split products really ran on the tensor cores: a plain-TF32 product would be ~1e-2 off at T = 0.07
+    assert np.abs(res["auto"][0] - res["simt"][0]).max() < 1e-4
