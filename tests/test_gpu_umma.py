@@ -251,6 +251,6 @@ def test_patchnce_tensor_core_3xtf32(orc):
     np.testing.assert_allclose(res["simt"][0], want, atol=1e-4)
     np.testing.assert_allclose(res["auto"][0], want, atol=1e-4)
     np.testing.assert_allclose(res["auto"][0], res["simt"][0], atol=2e-5)
-    np.testing.assert_allclose(res["auto"][1], res["simt"][1], atol=2e-5 * np.abs(res["simt"][1]).max())
+    np.testing.assert_allclose(res["auto"][1], res["simt"][1], atol=1e-4 * np.abs(res["simt"][1]).max())
     # the split products really ran on the tensor cores: a plain-TF32 product would be ~1e-2 off at T = 0.07
     assert np.abs(res["auto"][0] - res["simt"][0]).max() < 1e-4
