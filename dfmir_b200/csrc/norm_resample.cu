@@ -49,6 +49,15 @@ in_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, int HW, 
   }
 }
 
+// sums[i] = sum over chunks of partials[chunk][i]  (i < 2*N*C), chunks summed in a fixed order (deterministic)
+__global__ void in_sum_partials_kernel(const double* __restrict__ partials, double* __restrict__ sums, int n2, int nch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  double a = 0;
+  for (int c = 0; c < nch; ++c) a += partials[(long long)c * n2 + i];
+  sums[i] = a;
+}
+
 // stats[(n*C + c)*2] = mean, [..+1] = 1/sqrt(var + eps)  (biased variance, as F.instance_norm)
 __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __restrict__ stats, int NC, int HW,
                                    float eps) {
@@ -184,9 +193,10 @@ in_stats_v4_kernel(const float4* __restrict__ x, double* __restrict__ sums, int 
     for (int l = 1; l < npl; ++l)
 #pragma unroll
       for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[l * C4 + c4][j];
-    double* o = sums + ((long long)n * C4 * 4 + c4 * 4) * 2;
+    // per-CTA partial sums (no atomics, no zero-fill): in_sum_partials_kernel adds the gridDim.x chunks
+    double* o = sums + (((long long)blockIdx.x * gridDim.y + n) * C4 * 4 + c4 * 4) * 2;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(o + j, red[threadIdx.x][j]);
+    for (int j = 0; j < 8; ++j) o[j] = red[threadIdx.x][j];
   }
 }
 
@@ -301,9 +311,10 @@ in_bwd_reduce_v4_kernel(const float4* __restrict__ dy, const float4* __restrict_
     for (int l = 1; l < npl; ++l)
 #pragma unroll
       for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[l * C4 + c4][j];
-    double* o = sums + ((long long)n * C4 * 4 + c4 * 4) * 2;
+    // per-CTA partial sums (no atomics, no zero-fill): in_sum_partials_kernel adds the gridDim.x chunks
+    double* o = sums + (((long long)blockIdx.x * gridDim.y + n) * C4 * 4 + c4 * 4) * 2;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(o + j, red[threadIdx.x][j]);
+    for (int j = 0; j < 8; ++j) o[j] = red[threadIdx.x][j];
   }
 }
 
@@ -601,7 +612,10 @@ upcat_bwd_kernel(const float* __restrict__ dy, float* __restrict__ da, float* __
 
 }  // namespace
 
-extern "C" size_t dfmir_instnorm_workspace_bytes(int N, int C) { return sizeof(double) * 2 * (size_t)N * C + 256; }
+// [sums: 2*N*C doubles][per-CTA partials: chunks * 2*N*C doubles, chunks * N <= 8 * SMs + 2 * N]
+extern "C" size_t dfmir_instnorm_workspace_bytes(int N, int C) {
+  return sizeof(double) * 2 * (size_t)C * ((size_t)N + 8 * (size_t)dfmir_num_sms() + 2 * (size_t)N) + 256;
+}
 
 static int in_chunk(int HW, int N, int* nchunks) {
   // enough CTAs for ~8 per SM (full occupancy at 256 threads), at least 128 pixels per CTA
@@ -621,11 +635,17 @@ extern "C" int dfmir_instnorm_fwd(const float* x, const float* res, float* y, fl
   DFMIR_CHECK_ARG(ws_bytes >= dfmir_instnorm_workspace_bytes(N, C), "dfmir_instnorm_fwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   double* sums = (double*)ws;
-  DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  double* partials = sums + 2 * (size_t)N * C;
   int nch; const int chunk = in_chunk(H * W, N, &nch);
   const bool v4 = in_v4_ok(C, x, y, res, stats) && N <= 65535 && H + 2 * out_pad <= 65535;
-  if (v4) in_stats_v4_kernel<<<dim3(nch, N), 256, 0, st>>>((const float4*)x, sums, H * W, C / 4, chunk);
-  else in_stats_kernel<<<dim3(nch, N), 256, 0, st>>>(x, sums, H * W, C, chunk);
+  if (v4) {
+    in_stats_v4_kernel<<<dim3(nch, N), 256, 0, st>>>((const float4*)x, partials, H * W, C / 4, chunk);
+    DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(stats)");
+    in_sum_partials_kernel<<<(2 * N * C + 255) / 256, 256, 0, st>>>(partials, sums, 2 * N * C, nch);
+  } else {
+    DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
+    in_stats_kernel<<<dim3(nch, N), 256, 0, st>>>(x, sums, H * W, C, chunk);
+  }
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(stats)");
   in_finalize_kernel<<<(N * C + 255) / 256, 256, 0, st>>>(sums, stats, N * C, H * W, eps);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(finalize)");
@@ -649,20 +669,23 @@ extern "C" int dfmir_instnorm_bwd(const float* dy, const float* x, const float* 
   DFMIR_CHECK_ARG(ws_bytes >= dfmir_instnorm_workspace_bytes(N, C), "dfmir_instnorm_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   double* sums = (double*)ws;
-  DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  double* partials = sums + 2 * (size_t)N * C;
   if (dres && res_pad > 0)
     DFMIR_CUDA(cudaMemsetAsync(dres, 0, sizeof(float) * (size_t)N * (H + 2 * res_pad) * (W + 2 * res_pad) * C, st));
   int nch; const int chunk = in_chunk(H * W, N, &nch);
   const bool v4 = in_v4_ok(C, x, dy, dx, dres) && (((uintptr_t)stats) & 15) == 0 && N <= 65535;
   if (v4) {
     in_bwd_reduce_v4_kernel<<<dim3(nch, N), 256, 0, st>>>((const float4*)dy, (const float4*)x, (const float4*)stats, (float4*)dx,
-                                                          (float4*)dres, sums, H, W, C / 4, relu, out_pad, res_pad, chunk);
+                                                          (float4*)dres, partials, H, W, C / 4, relu, out_pad, res_pad, chunk);
     DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(reduce)");
+    in_sum_partials_kernel<<<(2 * N * C + 255) / 256, 256, 0, st>>>(partials, sums, 2 * N * C, nch);
+    DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(sum)");
     int ach; const int achunk = apply_chunk(H * W, N, &ach);
     in_bwd_apply_v4_kernel<<<dim3(ach, N), 256, 0, st>>>((const float4*)x, (const float4*)stats, sums, (float4*)dx, H * W, C / 4, achunk);
     DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(apply)");
     return DFMIR_OK;
   }
+  DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
   in_bwd_reduce_kernel<<<dim3(nch, N), 256, 0, st>>>(dy, x, stats, dx, dres, sums, H, W, C, relu, out_pad, res_pad, chunk);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(reduce)");
   in_bwd_apply_kernel<<<ew_grid((long long)N * H * W * C), 256, 0, st>>>(x, stats, sums, dx, N, H * W, C);
