@@ -1,6 +1,8 @@
-// K1 weight gradient on the 5th-generation tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in
-// TMEM, operands staged by TMA), for the 2-D stride-1 convolutions of ResnetGenerator
-// (models/networks.py:995,1016,1201,1214 — the backward of the cuDNN wgrad engines).
+// K1 / K2 weight gradient on the 5th-generation tensor cores (tcgen05.mma kind::tf32, fp32 accumulators in
+// TMEM, operands staged by TMA), for the stride-1 convolutions of ResnetGenerator (models/networks.py:995,
+// 1016,1201,1214) and of VoxelMorph's U-Net in 2-D and 3-D (vxm networks.py:1515) — the backward of the
+// cuDNN wgrad engines.  Channel counts that do not fill a tile are padded by the TMA unit's zero fill
+// (M side to 128 channels, N side to 32 / 64 / 128 / 256).
 //
 //   dW[tap][ci][co] = sum over output pixels p of  x[p + tap - pad][ci] * dy[p][co]
 //
@@ -26,19 +28,25 @@
 namespace {
 using namespace umma;
 
-constexpr int PIX = 32;                 // pixels (K) per pipeline stage
+constexpr int PIX = 32;                 // voxels (K) per pipeline stage
 constexpr int CHUNK_BYTES = PIX * 128;  // one 32-channel column group of a stage
 constexpr int UMMA_K = 8;               // tf32
 
 struct WgradP {
-  int N, H, W;              // dy: samples and spatial size (output of the forward conv)
+  int N, D, H, W;           // dy: samples and spatial size (output of the forward conv); 2-D: D = 1
   int Cin, Cout;
-  int KW, pad_h, pad_w;
-  int TW, TH, tiles_w, tiles_h;
+  int KH, KW, pad_d, pad_h, pad_w;
+  int TD, TH, TW, tiles_d, tiles_h, tiles_w;   // voxel chunk box (TD*TH*TW = 32) and chunks per axis
   int nchunks;
   int x_is_m;               // 1: M = input channels (x), N = output channels (dy); 0: swapped
   int m_tiles, n_tiles;
 };
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 
 template <int BN, int STAGES>
 struct WgLayout {
@@ -65,10 +73,12 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const int tap = blockIdx.x;
   const int mt = blockIdx.y / p.n_tiles, nt = blockIdx.y - mt * p.n_tiles;
   const int split = blockIdx.z, S = gridDim.z;
-  const int r = tap / p.KW, q = tap - r * p.KW;
-  const int dh = r - p.pad_h, dwv = q - p.pad_w;      // x pixel = dy pixel + (dh, dw)
+  const int q = tap % p.KW; const int t2 = tap / p.KW;
+  const int r = t2 % p.KH, kd = t2 / p.KH;
+  const int dd = kd - p.pad_d, dh = r - p.pad_h, dwv = q - p.pad_w;      // x voxel = dy voxel + (dd, dh, dw)
   const int m0 = mt * 128, n0 = nt * BN;
   const int iters = (p.nchunks - split + S - 1) / S;   // host guarantees S <= nchunks
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX); prefetch_tmap(&tmG);
@@ -76,7 +86,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)BN);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -86,23 +96,27 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (lane == 0) {
       const CUtensorMap* mapM = p.x_is_m ? &tmX : &tmG;
       const CUtensorMap* mapN = p.x_is_m ? &tmG : &tmX;
-      const int mdh = p.x_is_m ? dh : 0, mdw = p.x_is_m ? dwv : 0;
-      const int ndh = p.x_is_m ? 0 : dh, ndw = p.x_is_m ? 0 : dwv;
+      const int mdd = p.x_is_m ? dd : 0, mdh = p.x_is_m ? dh : 0, mdw = p.x_is_m ? dwv : 0;
+      const int ndd = p.x_is_m ? 0 : dd, ndh = p.x_is_m ? 0 : dh, ndw = p.x_is_m ? 0 : dwv;
+      const int tiles_hw = p.tiles_h * p.tiles_w;
+      const int tiles_img = p.tiles_d * tiles_hw;
       for (int it = 0; it < iters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        int c = split + it * S;
-        const int tw_i = c % p.tiles_w; c /= p.tiles_w;
-        const int th_i = c % p.tiles_h; const int n = c / p.tiles_h;
-        const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+        const int c = split + it * S;
+        const int n = c / tiles_img; int rem = c - n * tiles_img;
+        const int td_i = rem / tiles_hw; rem -= td_i * tiles_hw;
+        const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        const int d0 = td_i * p.TD, h0 = th_i * p.TH, w0 = tw_i * p.TW;
         mbar_wait(empty + s, ph ^ 1);
         uint8_t* sa = smem + s * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         mbar_expect_tx(full + s, (uint32_t)L::STAGE_BYTES);
+        // channel groups beyond the tensor's channel count are zero-filled by the TMA unit (M padded to 128)
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tma_load_4d(sa + g * CHUNK_BYTES, mapM, full + s, m0 + g * 32, w0 + mdw, h0 + mdh, n);
+        for (int g = 0; g < 4; ++g) tma_load_5d(sa + g * CHUNK_BYTES, mapM, full + s, m0 + g * 32, w0 + mdw, h0 + mdh, d0 + mdd, n);
 #pragma unroll
-        for (int g = 0; g < BN / 32; ++g) tma_load_4d(sb + g * CHUNK_BYTES, mapN, full + s, n0 + g * 32, w0 + ndw, h0 + ndh, n);
+        for (int g = 0; g < BN / 32; ++g) tma_load_5d(sb + g * CHUNK_BYTES, mapN, full + s, n0 + g * 32, w0 + ndw, h0 + ndh, d0 + ndd, n);
       }
     }
   } else if (warp == 1) {
@@ -118,7 +132,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const uint64_t bdesc = smem_desc(sa + L::A_BYTES, CHUNK_BYTES, 512, LAYOUT_SW128_BASE32B);
 #pragma unroll
         for (int k = 0; k < PIX / UMMA_K; ++k) {
-          // next 8 pixels: +1024 bytes = +64 in 16-byte address units
+          // next 8 voxels: +1024 bytes = +64 in 16-byte address units
           umma_tf32(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (it | k) != 0);
         }
         umma_commit(empty + s);
@@ -129,6 +143,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     // epilogue: thread = accumulator row (M index); 32 consecutive N columns per TMEM load
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int CM = p.x_is_m ? p.Cin : p.Cout, CN = p.x_is_m ? p.Cout : p.Cin;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     float* dwt = dw + (long long)tap * p.Cin * p.Cout;
@@ -136,24 +151,32 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      if (m0 + row >= CM || n0 + c0 >= CN) continue;
       if (p.x_is_m) {
         float* dst = dwt + (long long)(m0 + row) * p.Cout + n0 + c0;     // row = ci, columns = co (contiguous)
+        if (n0 + c0 + 32 <= CN && (p.Cout & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < CN) atomicAdd(dst + j, v[j]);
+        }
       } else {
         float* dst = dwt + (long long)(n0 + c0) * p.Cout + m0 + row;     // row = co (coalesced over lanes), columns = ci
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + (long long)j * p.Cout, v[j]);
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c0 + j < CN) atomicAdd(dst + (long long)j * p.Cout, v[j]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)BN);
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// db[c] += sum over pixels of dy[pixel][c]  (dy channels-last, contiguous pixels x C; C in {64,128,256}).
-// thread = (channel, pixel lane); 4 independent accumulators keep 4 loads in flight per thread.
+// db[c] += sum over voxels of dy[voxel][c]  (dy channels-last, contiguous voxels x C; C <= 256).
+// thread = (channel, voxel lane); 4 independent accumulators keep 4 loads in flight per thread.
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, long long pixels, int C, long long per_block) {
   __shared__ float part[256];
@@ -163,14 +186,16 @@ bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, long long
   const long long p0 = (long long)blockIdx.x * per_block;
   const long long p1 = min(pixels, p0 + per_block);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  long long px = p0 + pl;
-  for (; px + 3LL * lanes < p1; px += 4LL * lanes) {
-    a0 += __ldg(dy + px * C + c);
-    a1 += __ldg(dy + (px + lanes) * C + c);
-    a2 += __ldg(dy + (px + 2LL * lanes) * C + c);
-    a3 += __ldg(dy + (px + 3LL * lanes) * C + c);
+  if (pl < lanes) {
+    long long px = p0 + pl;
+    for (; px + 3LL * lanes < p1; px += 4LL * lanes) {
+      a0 += __ldg(dy + px * C + c);
+      a1 += __ldg(dy + (px + lanes) * C + c);
+      a2 += __ldg(dy + (px + 2LL * lanes) * C + c);
+      a3 += __ldg(dy + (px + 3LL * lanes) * C + c);
+    }
+    for (; px < p1; px += lanes) a0 += __ldg(dy + px * C + c);
   }
-  for (; px < p1; px += lanes) a0 += __ldg(dy + px * C + c);
   float acc = (a0 + a1) + (a2 + a3);
   part[t] = acc;
   __syncthreads();
@@ -180,15 +205,22 @@ bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, long long
   }
 }
 
+inline int ceil_bn(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : 256)); }
+
+// operand roles: the M side is padded to multiples of 128 channels, the N side to its tile width; pick the
+// assignment with the smaller padded product (ties: x on the M side, whose epilogue is vectorised)
+inline int pick_x_is_m(int Cin, int Cout) {
+  const long long cx = (long long)((Cin + 127) / 128 * 128) * ((Cout + ceil_bn(Cout) - 1) / ceil_bn(Cout) * ceil_bn(Cout));
+  const long long cg = (long long)((Cout + 127) / 128 * 128) * ((Cin + ceil_bn(Cin) - 1) / ceil_bn(Cin) * ceil_bn(Cin));
+  return cx <= cg;
+}
+
 int wgrad_supported(const dfmir_conv_desc* d) {
-  if (!d || d->nd != 2 || d->stride != 1) return 0;
-  const int Cin = d->Cin, Cout = d->Cout;
-  const bool ok_x_m = (Cin % 128 == 0) && (Cout == 64 || Cout == 128 || Cout % 256 == 0);
-  const bool ok_g_m = (Cout % 128 == 0) && (Cin == 64 || Cin == 128 || Cin % 256 == 0);
-  if (!ok_x_m && !ok_g_m) return 0;
-  const long long* xs = d->x_strides; const long long* ys = d->y_strides;
-  if (xs[3] != 1 || ys[3] != 1) return 0;
-  for (int i = 0; i < 3; ++i) if ((xs[i] & 3) || (ys[i] & 3)) return 0;
+  if (!d || (d->nd != 2 && d->nd != 3) || d->stride != 1) return 0;
+  if (d->Cin % 4 || d->Cout % 4 || d->Cin < 16 || d->Cout < 16) return 0;   // rows of both operands: 16-byte multiples
+  const int nd = d->nd;
+  if (d->x_strides[nd + 1] != 1 || d->y_strides[nd + 1] != 1) return 0;
+  for (int i = 0; i <= nd; ++i) if ((d->x_strides[i] & 3) || (d->y_strides[i] & 3)) return 0;
   return 1;
 }
 
@@ -203,61 +235,83 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmG, float* dw, cons
   return DFMIR_OK;
 }
 
+// 5-D tiled map over a channels-last activation, box {32 ch, TW, TH, TD, 1}, MN-major TF32 swizzle
+int encode_map5(CUtensorMap* tm, const float* act, const long long* st, int nd, int C, const int* shape, int N, int TW, int TH,
+                int TD, const char* who) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
+  if ((uintptr_t)act & 15) { dfmir_set_error("%s: TMA needs a 16-byte aligned base pointer", who); return DFMIR_ERR_ARG; }
+  const int D = nd == 3 ? shape[0] : 1, H = shape[nd - 2], W = shape[nd - 1];
+  const long long sn = st[0], sw = st[nd], sh = st[nd - 1], sd = nd == 3 ? st[1] : sh * H;
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)sw * 4, (cuuint64_t)sh * 4, (cuuint64_t)sd * 4, (cuuint64_t)sn * 4};
+  cuuint32_t box[5] = {32, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TD, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  return DFMIR_OK;
+}
+
 }  // namespace
 
 extern "C" int dfmir_conv_umma_wgrad_supported(const dfmir_conv_desc* d) { return wgrad_supported(d); }
 
 // Weight / bias gradient on the tensor cores.  dw [tap][Cin][Cout] and db [Cout] (nullable) are
-// ACCUMULATED into (zero-fill them first).  dy must be channels-last with unit channel stride.
+// ACCUMULATED into (zero-fill them first).  x and dy channels-last with unit channel stride.
 extern "C" int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d,
                                      void* stream) {
   const char* who = "dfmir_conv_umma_wgrad";
   if (!wgrad_supported(d)) {
-    dfmir_set_error("%s: needs a 2-D stride-1 convolution with one channel count a multiple of 128 and the other in "
-                    "{64,128,256k}, channels-last operands", who);
+    dfmir_set_error("%s: needs a 2-D / 3-D stride-1 convolution with channel counts that are multiples of 4 and >= 16 on "
+                    "channels-last operands with 16-byte aligned strides", who);
     return DFMIR_ERR_UNSUPPORTED;
   }
   DFMIR_CHECK_ARG(x && dy && dw, "%s: null pointer", who);
   cudaStream_t st = (cudaStream_t)stream;
+  const int nd = d->nd;
   WgradP p;
-  p.N = d->N; p.H = d->out_shape[0]; p.W = d->out_shape[1];
+  p.N = d->N; p.D = nd == 3 ? d->out_shape[0] : 1; p.H = d->out_shape[nd - 2]; p.W = d->out_shape[nd - 1];
   p.Cin = d->Cin; p.Cout = d->Cout;
-  p.KW = d->kernel[1]; p.pad_h = d->pad[0]; p.pad_w = d->pad[1];
+  p.KH = d->kernel[nd - 2]; p.KW = d->kernel[nd - 1];
+  p.pad_d = nd == 3 ? d->pad[0] : 0; p.pad_h = d->pad[nd - 2]; p.pad_w = d->pad[nd - 1];
   int TW = PIX;
   while (TW > p.W && TW > 8) TW >>= 1;
-  p.TW = TW; p.TH = PIX / TW;
+  p.TW = TW; p.TH = PIX / TW; p.TD = 1;
+  if (p.TH > p.H && p.D > 1) { p.TD = p.TH; p.TH = 1; }     // narrow 3-D volumes: take the rest of the chunk along depth
   p.tiles_w = (p.W + p.TW - 1) / p.TW;
   p.tiles_h = (p.H + p.TH - 1) / p.TH;
-  p.nchunks = p.N * p.tiles_h * p.tiles_w;
+  p.tiles_d = (p.D + p.TD - 1) / p.TD;
+  p.nchunks = p.N * p.tiles_d * p.tiles_h * p.tiles_w;
   if (p.nchunks == 0) return DFMIR_OK;
-  // operand roles: prefer x on the M side (vectorised epilogue)
-  p.x_is_m = (d->Cin % 128 == 0) && (d->Cout == 64 || d->Cout == 128 || d->Cout % 256 == 0);
+  p.x_is_m = pick_x_is_m(d->Cin, d->Cout);
   const int CM = p.x_is_m ? d->Cin : d->Cout, CN = p.x_is_m ? d->Cout : d->Cin;
-  const int BN = CN >= 256 ? 256 : CN;
-  p.m_tiles = CM / 128; p.n_tiles = CN / BN;
-  const int taps = d->kernel[0] * d->kernel[1];
+  const int BN = ceil_bn(CN);
+  p.m_tiles = (CM + 127) / 128; p.n_tiles = (CN + BN - 1) / BN;
+  int taps = 1;
+  for (int a = 0; a < nd; ++a) taps *= d->kernel[a];
   const int tiles = taps * p.m_tiles * p.n_tiles;
   int S = dfmir_num_sms() / tiles;
   if (S < 1) S = 1;
   if (S > p.nchunks) S = p.nchunks;
 
   CUtensorMap tmX, tmG;
-  int rc = encode_act_map(&tmX, x, d->x_strides, d->Cin, d->in_shape[1], d->in_shape[0], d->N, p.TW, p.TH, who,
-                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  int rc = encode_map5(&tmX, x, d->x_strides, nd, d->Cin, d->in_shape, d->N, p.TW, p.TH, p.TD, who);
   if (rc) return rc;
-  rc = encode_act_map(&tmG, dy, d->y_strides, d->Cout, d->out_shape[1], d->out_shape[0], d->N, p.TW, p.TH, who,
-                      CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  rc = encode_map5(&tmG, dy, d->y_strides, nd, d->Cout, d->out_shape, d->N, p.TW, p.TH, p.TD, who);
   if (rc) return rc;
   if (BN == 256) rc = launch_wgrad<256>(tmX, tmG, dw, p, taps, S, st);
   else if (BN == 128) rc = launch_wgrad<128>(tmX, tmG, dw, p, taps, S, st);
-  else rc = launch_wgrad<64>(tmX, tmG, dw, p, taps, S, st);
+  else if (BN == 64) rc = launch_wgrad<64>(tmX, tmG, dw, p, taps, S, st);
+  else rc = launch_wgrad<32>(tmX, tmG, dw, p, taps, S, st);
   if (rc) return rc;
   if (db) {
-    const long long pixels = (long long)d->N * p.H * p.W;
-    // dy contiguous (N,H,W,Cout) is required for the bias reduction
-    DFMIR_CHECK_ARG(d->y_strides[2] == d->Cout && d->y_strides[1] == (long long)p.W * d->Cout &&
-                    d->y_strides[0] == (long long)p.H * p.W * d->Cout, "%s: bias gradient needs a contiguous dy", who);
-    DFMIR_CHECK_ARG(d->Cout == 64 || d->Cout == 128 || d->Cout == 256, "%s: bias gradient covers Cout in {64,128,256}", who);
+    long long pixels = d->N, dense = d->Cout;
+    bool contiguous = d->y_strides[nd + 1] == 1;
+    for (int a = nd - 1; a >= 0; --a) { contiguous = contiguous && d->y_strides[1 + a] == dense; dense *= d->out_shape[a]; pixels *= d->out_shape[a]; }
+    contiguous = contiguous && d->y_strides[0] == dense;
+    DFMIR_CHECK_ARG(contiguous, "%s: bias gradient needs a contiguous dy", who);
+    DFMIR_CHECK_ARG(d->Cout <= 256, "%s: bias gradient covers Cout <= 256", who);
     int blocks = 16 * dfmir_num_sms();
     long long per_block = (pixels + blocks - 1) / blocks;
     if (per_block < 32) per_block = 32;
