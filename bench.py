@@ -349,16 +349,18 @@ def run_ours_3d(args):
     line = {
         "metric": METRIC, "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "tf32", "data": "synthetic",
         "config": {"workload": f"3D {S}^3 batch={B}/GPU VoxelMorph-3D (6-level) + VecInt + NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[2])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "arithmetic": "fp32 CUDA cores (the 2..64-channel 3-D convolutions have no tensor-core kernel yet)",
+                   "arithmetic": "fp32 storage; stride-1 convolutions with >= 16 channels on tcgen05 kind::tf32 (forward, data and weight "
+                                 "gradient, 5-D TMA boxes); the stride-2 encoder, the 2-channel first layer and the backward of the planar "
+                                 "flow head on fp32 CUDA cores; warp / VecInt / NCC / Grad fp32",
                    "l2_policy": "inputs larger than L2: full-resolution activations are 34 channels x 8 MB per volume"},
         "clocks": clocks,
         "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * B * S ** 3 * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv_simt_kernel / conv_wgrad_simt_kernel (fp32 implicit GEMM, all layers of the step)",
+        "roofline": {"bound": "tensor", "kernel": "all convolution kernels of the step (conv_umma_halo_kernel, conv_wgrad_umma_kernel, fp32 kernels for the strided / thin layers)",
                      "achieved": flops * args.steps / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": flops * args.steps / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
                      "peak_source": f"bf16_tflops_sustained, {pk_src}; whole-step algorithmic conv FLOPs over step time (not a single kernel)",
