@@ -267,7 +267,9 @@ int dfmir_thin_fwd(const float* x, const float* w, const float* bias, float* y, 
     if (d->y_strides[3] != 1) return 0;
     p.C = d->Cout; p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 31) / 32;
     const unsigned gx = (unsigned)(p.N * p.tiles_h * p.tiles_w);
-    if (p.C > 16) thin::thin_expand_kernel<7, 64><<<dim3(gx, (p.C + 63) / 64), 256, 0, st>>>(x, w, bias, y, p);
+    // 32 output channels per thread (two CTAs per pixel tile for the 64-channel stem): 3 CTAs resident per SM
+    // instead of 1 with 64 accumulators per thread
+    if (p.C > 16) thin::thin_expand_kernel<7, 32><<<dim3(gx, (p.C + 31) / 32), 256, 0, st>>>(x, w, bias, y, p);
     else thin::thin_expand_kernel<7, 16><<<dim3(gx, 1), 256, 0, st>>>(x, w, bias, y, p);
   } else {
     if (!vec4_ok(x, d->x_strides, d->Cin) || (((uintptr_t)w) & 15)) return 0;
@@ -293,7 +295,7 @@ int dfmir_thin_dgrad(const float* dy, const float* wt, float* dx, const dfmir_co
     if (d->x_strides[3] != 1) return 0;
     p.C = d->Cin; p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 31) / 32;
     const unsigned gx = (unsigned)(p.N * p.tiles_h * p.tiles_w);
-    if (p.C > 16) thin::thin_expand_kernel<7, 64><<<dim3(gx, (p.C + 63) / 64), 256, 0, st>>>(dy, wt, nullptr, dx, p);
+    if (p.C > 16) thin::thin_expand_kernel<7, 32><<<dim3(gx, (p.C + 31) / 32), 256, 0, st>>>(dy, wt, nullptr, dx, p);
     else thin::thin_expand_kernel<7, 16><<<dim3(gx, 1), 256, 0, st>>>(dy, wt, nullptr, dx, p);
   } else {                   // stem: dy has Cout channels, dx has one
     if (!vec4_ok(dy, d->y_strides, d->Cout) || (((uintptr_t)wt) & 15)) return 0;
