@@ -275,9 +275,13 @@ def run_ours_3d(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from dfmir_b200 import _lib, vxm
-    B, S = args.batch3d, args.size3d
+    B = args.batch3d
+    shape = tuple(int(v) for v in args.shape3d.split(",")) if args.shape3d else (args.size3d,) * 3
+    vox = shape[0] * shape[1] * shape[2]
+    six_level = args.features3d == "6level"
     torch.manual_seed(1234)
-    R = vxm.VxmDense((S, S, S), [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]], int_steps=7, bidir=False).cuda()
+    feats = [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]] if six_level else None   # None: vxm/networks.py:9-14 defaults
+    R = vxm.VxmDense(shape, feats, int_steps=7, bidir=False).cuda()
     params = [p for p in R.parameters() if p.requires_grad]
     flat = None
     if world > 1:
@@ -290,7 +294,7 @@ def run_ours_3d(args):
     optim = torch.optim.Adam(params, lr=2e-4, betas=(0.5, 0.999))
     g = torch.Generator().manual_seed(77 + rank)
     def vol():
-        x = torch.randn(B, 1, S, S, S, generator=g)
+        x = torch.randn(B, 1, *shape, generator=g)
         k = torch.ones(1, 1, 5, 5, 5) / 125.0
         for _ in range(2):
             x = torch.nn.functional.conv3d(x, k, padding=2)
@@ -344,13 +348,18 @@ def run_ours_3d(args):
     clocks = sampler.stop() if sampler else None
     if rank != 0:
         return
-    flops = 284.6e9 * B      # VxmDense-3D 128^3 6-level, fwd 95.0 + bwd 189.6 GFLOP per pair
+    # VxmDense-3D 128^3 6-level 284.6 GFLOP per pair (95.0 fwd + 189.6 bwd); default features at
+    # 160x192x160 1708.1; both scale with the voxel count
+    flops = (284.6e9 * vox / 128 ** 3 if six_level else 1708.1e9 * vox / (160 * 192 * 160)) * B
+    name = "x".join(str(v) for v in shape)
+    cfg_no = 3 if shape == (160, 192, 160) else 2
     pk, pk_src = peaks()
     line = {
         "metric": METRIC, "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32", "data": "synthetic",
-        "config": {"workload": f"3D {S}^3 batch={B}/GPU VoxelMorph-3D (6-level) + VecInt + NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[2])",
+        "config": {"workload": f"3D {name} batch={B}/GPU VoxelMorph-3D ({'6-level' if six_level else 'default'} features) + VecInt + "
+                               f"NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[{cfg_no}])",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "arithmetic": "fp32 storage; stride-1 convolutions with >= 16 channels on tcgen05 kind::tf32 (forward, data and weight "
                                  "gradient, 5-D TMA boxes); the stride-2 encoder, the 2-channel first layer and the backward of the planar "
@@ -358,7 +367,7 @@ def run_ours_3d(args):
                    "l2_policy": "inputs larger than L2: full-resolution activations are 34 channels x 8 MB per volume"},
         "clocks": clocks,
         "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(2 * B * S ** 3 * 4), "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": int(2 * B * vox * 4), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "all convolution kernels of the step (conv_umma_halo_kernel, conv_wgrad_umma_kernel, fp32 kernels for the strided / thin layers)",
                      "achieved": flops * args.steps / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -384,6 +393,9 @@ def main():
                     help="2d: BASELINE configs[1] (the headline line, default); 3d: configs[2], VoxelMorph-3D 128^3")
     ap.add_argument("--batch3d", type=int, default=2)
     ap.add_argument("--size3d", type=int, default=128)
+    ap.add_argument("--shape3d", default="", help="D,H,W of the 3-D workload (overrides --size3d), e.g. 160,192,160 for configs[3]")
+    ap.add_argument("--features3d", default="6level", choices=["6level", "default"],
+                    help="VoxelMorph-3D U-Net features: the 6-level list of configs[2] or the reference defaults (configs[3])")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

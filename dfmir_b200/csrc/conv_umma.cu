@@ -28,6 +28,7 @@
 // warps 2..9 = epilogue (TMEM -> registers -> bias/activation -> global, one pixel row per thread;
 // two warps share each TMEM lane quarter and split the sub-tiles).
 // The data gradient is the same kernel run on dy with taps flipped and pad' = k-1-pad.
+#include <type_traits>
 #include "umma.cuh"
 #include "dfmir_b200.h"
 #include <stdlib.h>
@@ -66,20 +67,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 template <int BN, int MT, int STAGES, int AS>
 struct SmemLayout {
   static_assert(MT * BN * AS <= 512, "TMEM has 512 columns");
@@ -261,6 +248,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // are exactly (8*SW+KW-1) rows apart.  Activation traffic per output voxel drops from taps x 128 B to
 // ~1.3-2 x 128 B per chunk (9x / 27x fewer L2 -> shared-memory bytes in 2-D / 3-D); the weights stream as
 // before, one {32, BN} box per (tap, chunk) through their own deeper pipeline.
+// compile-time loop: f(integral_constant<int, I>) for I = 0 .. N-1 (#pragma unroll leaves loops around mbarrier waits rolled)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
 template <int BN, int SD, int SH, int SW, int BST>
 struct HaloCfg {
   static constexpr int MT = SD * SH * SW;
@@ -274,7 +270,11 @@ struct HaloP {
   int a_bytes;             // bytes of one activation stage (rows * 128, rounded up to 1024)
 };
 
-template <int BN, int SD, int SH, int SW, int BST>
+// KDT > 0: the kernel is 3 x 3 with depth KDT (1 or 3), known at compile time: the tap loops of the TMA and MMA
+// threads unroll completely and every descriptor is the stage's base descriptor plus a constant, which keeps the
+// single MMA-issuing thread at ~6 instructions per tcgen05.mma (with run-time kernel extents it spent ~270
+// instructions per tap and the tensor pipe waited for it: 59 % active on the ResnetBlock conv).  KDT = 0: any extents.
+template <int BN, int SD, int SH, int SW, int BST, int KDT>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const float* __restrict__ bias, float* __restrict__ y, const HaloP hp) {
@@ -319,6 +319,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       // ---------------- TMA producer
       uint32_t ia = 0, ib = 0;
+      int sbp = 0; uint32_t bphp = 0;              // weight stage / phase counters of the unrolled variant
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int nt = item % n_tiles, pt = item / n_tiles;
         const int n = pt / tiles_per_img; int rem = pt - n * tiles_per_img;
@@ -330,11 +331,20 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(a_empty + sa, ((ia >> 1) & 1) ^ 1);
           mbar_expect_tx(a_full + sa, (uint32_t)(hp.HD * hp.HH * hp.HW * 128));
           tma_load_5d(sA + sa * hp.a_bytes, &tmA, a_full + sa, cc * KCH, w0 - p.pad_w, h0 - p.pad_h, d0 - p.pad_d, n);
-          for (int tap = 0; tap < taps; ++tap, ++ib) {
-            const int sb = ib % BST;
-            mbar_wait(b_empty + sb, ((ib / BST) & 1) ^ 1);
-            mbar_expect_tx(b_full + sb, (uint32_t)C::B_BYTES);
-            tma_load_3d(sB + sb * C::B_BYTES, &tmB, b_full + sb, cc * KCH, nt * BN, p.flip ? taps - 1 - tap : tap);
+          if constexpr (KDT > 0) {
+            for (int tap = 0; tap < KDT * 9; ++tap) {
+              mbar_wait(b_empty + sbp, bphp ^ 1);
+              mbar_expect_tx(b_full + sbp, (uint32_t)C::B_BYTES);
+              tma_load_3d(sB + sbp * C::B_BYTES, &tmB, b_full + sbp, cc * KCH, nt * BN, p.flip ? KDT * 9 - 1 - tap : tap);
+              if (++sbp == BST) { sbp = 0; bphp ^= 1; }
+            }
+          } else {
+            for (int tap = 0; tap < taps; ++tap, ++ib) {
+              const int sb = ib % BST;
+              mbar_wait(b_empty + sb, ((ib / BST) & 1) ^ 1);
+              mbar_expect_tx(b_full + sb, (uint32_t)C::B_BYTES);
+              tma_load_3d(sB + sb * C::B_BYTES, &tmB, b_full + sb, cc * KCH, nt * BN, p.flip ? taps - 1 - tap : tap);
+            }
           }
         }
       }
@@ -344,6 +354,8 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       // ---------------- MMA issuer
       constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
       const uint32_t sbo = (uint32_t)hp.HW * 128u;             // next h row of the halo tile
+      const uint64_t bdesc0 = smem_desc_sw128(smem_u32(sB), 16, 1024);
+      int sbm = 0; uint32_t bphm = 0;              // weight stage / phase counters of the unrolled variant
       uint32_t ia = 0, ib = 0, ti = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++ti) {
         const uint32_t as = ti % AS, aph = (ti / AS) & 1;
@@ -355,6 +367,38 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(a_full + sa, (ia >> 1) & 1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + sa * hp.a_bytes);
+          // a partial last chunk (Cin = 16, 36, ...) holds zero-filled channels: issue only the K slices with data
+          const int rem_c = p.Cin - cc * KCH;
+          const int ksteps = rem_c >= KCH ? KCH / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;
+          if constexpr (KDT > 0) {
+            constexpr int HH = 16 * SH + 2, HW = 8 * SW + 2;
+            const uint64_t adesc0 = smem_desc_sw128(a_base, 16, HW * 128);     // 8-row groups one halo row apart
+            auto issue = [&](auto full_c) {
+              constexpr bool FULL = decltype(full_c)::value;          // all four K slices of the chunk hold data
+              static_for<0, KDT * 9>([&](auto tap_c) {
+                constexpr int tap = decltype(tap_c)::value;
+                constexpr int kd = tap / 9, r = (tap / 3) % 3, q = tap % 3;
+                mbar_wait(b_full + sbm, bphm);
+                tc_fence_after();
+                const uint64_t bdesc = bdesc0 + (uint64_t)(sbm * (C::B_BYTES / 16));
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                  const int sw = j % SW, sh = (j / SW) % SH, sd = j / (SW * SH);
+                  const int row = ((sd + kd) * HH + 16 * sh + r) * HW + 8 * sw + q;      // compile-time constant
+                  const uint64_t adesc = adesc0 + (uint64_t)(8 * row);
+#pragma unroll
+                  for (int k = 0; k < KCH / UMMA_K; ++k)
+                    if (FULL || k < ksteps)
+                      umma_tf32(acc + j * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | k) != 0 ? 1u : (uint32_t)(cc != 0));
+                }
+                umma_commit(b_empty + sbm);
+                if (++sbm == BST) { sbm = 0; bphm ^= 1; }
+              });
+            };
+            if (ksteps == KCH / UMMA_K) issue(std::true_type{}); else issue(std::false_type{});
+            umma_commit(a_empty + sa);
+            continue;
+          }
           int tap = 0;
           for (int kd = 0; kd < p.KD; ++kd)
             for (int r = 0; r < p.KH; ++r)
@@ -370,7 +414,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                   const uint64_t adesc = smem_desc_sw128(a_base + row * 128u, 16, sbo);
 #pragma unroll
                   for (int k = 0; k < KCH / UMMA_K; ++k)
-                    umma_tf32(acc + j * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (cc | tap | k) != 0);
+                    if (k < ksteps) umma_tf32(acc + j * BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (cc | tap | k) != 0);
                 }
                 umma_commit(b_empty + sb);
               }
@@ -456,9 +500,9 @@ bool operand_ok(const long long* s, int nd) {     // TMA source: unit channel st
 int umma_shape_ok(const dfmir_conv_desc* d, int dgrad) {
   if (!d || (d->nd != 2 && d->nd != 3) || d->stride != 1) return 0;
   const int Cin = dgrad ? d->Cout : d->Cin, Cout = dgrad ? d->Cin : d->Cout;
-  // K side: rows of the weight matrix must be 16-byte multiples (Cin % 4), at least half a 32-channel chunk
-  // of useful work; N side: any count (padded to the tile by zero-filled weight rows)
-  if (Cin % 4 || Cin < 16 || Cout < 1) return 0;
+  // K side: rows of the weight matrix must be 16-byte multiples (Cin % 4; K slices that hold only zero-filled
+  // channels are not issued); N side: any count (padded to the tile by zero-filled weight rows)
+  if (Cin % 4 || Cin < 4 || Cout < 1) return 0;
   const long long* is = dgrad ? d->y_strides : d->x_strides;
   if (!operand_ok(is, d->nd)) return 0;
   for (int a = 0; a < d->nd; ++a) {
@@ -471,7 +515,7 @@ int umma_shape_ok(const dfmir_conv_desc* d, int dgrad) {
 int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
   if (!umma_shape_ok(d, dgrad)) {
     dfmir_set_error("%s: the tensor-core path covers 2-D / 3-D stride-1 convolutions whose reduction-side channel count is a "
-                    "multiple of 4 and >= 16, on channels-last operands with 16-byte aligned strides", who);
+                    "multiple of 4, on channels-last operands with 16-byte aligned strides", who);
     return DFMIR_ERR_UNSUPPORTED;
   }
   const int nd = d->nd, sh = 3 - nd;
@@ -524,8 +568,8 @@ int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
   return DFMIR_OK;
 }
 
-template <int BN, int SD, int SH, int SW, int BST>
-int launch_halo(const float* act, const Strides5& as, int ID, int IH, int IW, const CUtensorMap& tmB, const float* bias, float* y,
+template <int BN, int SD, int SH, int SW, int BST, int KDT>
+int launch_halo_k(const float* act, const Strides5& as, int ID, int IH, int IW, const CUtensorMap& tmB, const float* bias, float* y,
                 UmmaP p, cudaStream_t st, const char* who) {
   using C = HaloCfg<BN, SD, SH, SW, BST>;
   HaloP hp;
@@ -547,16 +591,27 @@ int launch_halo(const float* act, const Strides5& as, int ID, int IH, int IW, co
   CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(halo tile) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
-  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<BN, SD, SH, SW, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<BN, SD, SH, SW, BST, KDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = p.ptiles * ((p.Cout + BN - 1) / BN);
   if (items == 0) return DFMIR_OK;
   int grid = dfmir_num_sms();
   if (grid > items) grid = items;
   const int rounds = (items + grid - 1) / grid;
   grid = (items + rounds - 1) / rounds;
-  conv_umma_halo_kernel<BN, SD, SH, SW, BST><<<grid, THREADS, smem, st>>>(tmA, tmB, bias, y, hp);
+  conv_umma_halo_kernel<BN, SD, SH, SW, BST, KDT><<<grid, THREADS, smem, st>>>(tmA, tmB, bias, y, hp);
   DFMIR_CHECK_LAUNCH(who);
   return DFMIR_OK;
+}
+
+// 3 x 3 (x 3) kernels take the instantiation with compile-time taps; 2-D tile configurations have SD = 1
+template <int BN, int SD, int SH, int SW, int BST>
+int launch_halo(const float* act, const Strides5& as, int ID, int IH, int IW, const CUtensorMap& tmB, const float* bias, float* y,
+                UmmaP p, cudaStream_t st, const char* who) {
+  static const int fixed = getenv("DFMIR_UMMA_FIXED_TAPS") ? atoi(getenv("DFMIR_UMMA_FIXED_TAPS")) : 1;
+  constexpr int KDT = SD > 1 ? 3 : 1;
+  if (fixed && p.KH == 3 && p.KW == 3 && p.KD == KDT)
+    return launch_halo_k<BN, SD, SH, SW, BST, KDT>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+  return launch_halo_k<BN, SD, SH, SW, BST, 0>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
 }
 
 // act: source activation (channels-last, c stride 1) with element strides `as` and spatial size (ID, IH, IW)

@@ -175,6 +175,154 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------- halo variant (few-channel 3x3 / 3x3x3 layers)
+// The per-tap kernel above re-reads x and dy once per tap (27 times in 3-D) and pads the M side to 128
+// channels: right for the 256-channel ResnetBlock convs, 5 ms per launch for VoxelMorph-3D's full-resolution
+// 36 -> 32 layer.  Here a CTA owns ALL taps of a 32-input-channel chunk and walks tiles of TH x 32 output
+// voxels:
+//   * x arrives ONCE per tile as a box with its halo, {32 ch, 35, TH + 2, KD, 1} (zero-filled outside the volume =
+//     the convolution's zero padding), dy as {32 ch, 32, TH, 1, 1};
+//   * an MN-major operand may start at any 128-byte row (= voxel) of the TMA-written tile and its four
+//     32-channel column groups may be ONE row apart (leading byte offset 128; tools/umma_mn_shift_probe.cu), so
+//     the M = 128 operand of one MMA is [kw = 0..3] x [32 input channels]: three taps along w per instruction
+//     (the fourth column group is computed and dropped) instead of one tap with 96 zero-padded rows;
+//   * K = 8 consecutive voxels along w; an accumulator per (kd, kh): KD*3 accumulators of BN columns in TMEM,
+//     resident over the CTA's whole tile range, then one red.global.add pass (split-K over CTAs, dW zero-filled
+//     by the caller as for the other kernels).
+// grid = (S, input-channel chunks, output-channel tiles); 192 threads: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue.
+template <int BN, int KD>
+struct WgHalo {
+  static constexpr int TW = 32, TH = 4, KH = 3, KW = 3;
+  static constexpr int HW = TW + 3, HH = TH + KH - 1, HD = KD;
+  static constexpr int ROWS = HW * HH * HD;
+  static constexpr int X_BYTES = (ROWS * 128 + 1023) / 1024 * 1024;
+  static constexpr int G_BYTES = TH * TW * 128;
+  static constexpr int STAGE_BYTES = X_BYTES + G_BYTES;
+  static constexpr int STAGES = KD == 3 ? 2 : 4;
+  static constexpr int ACCS = KD * KH;
+  static constexpr int COLS = ACCS * BN;
+  static constexpr uint32_t TMEM_COLS = COLS <= 32 ? 32 : (COLS <= 64 ? 64 : (COLS <= 128 ? 128 : (COLS <= 256 ? 256 : 512)));
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static_assert(COLS <= 512, "TMEM has 512 columns");
+};
+
+struct WgHaloP {
+  int N, D, H, W, Cin, Cout;
+  int pad_d, pad_h, pad_w;
+  int tiles_h, tiles_w, ntiles;
+};
+
+template <int BN, int KD>
+__global__ void __launch_bounds__(192)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                       float* __restrict__ dw, const WgHaloP p) {
+  using L = WgHalo<BN, KD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + L::BAR_OFF);
+  uint64_t* empty = full + L::STAGES;
+  uint64_t* tmem_full = empty + L::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, S = gridDim.x;
+  const int c0 = blockIdx.y * 32, n0 = blockIdx.z * BN;
+  const int iters = (p.ntiles - split + S - 1) / S;      // host guarantees S <= ntiles
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmG);
+    for (int s = 0; s < L::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int tiles_hw = p.tiles_h * p.tiles_w;
+      const int tiles_img = p.D * tiles_hw;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % L::STAGES;
+        const uint32_t ph = (it / L::STAGES) & 1;
+        const int t = split + it * S;
+        const int n = t / tiles_img; int rem = t - n * tiles_img;
+        const int d0 = rem / tiles_hw; rem -= d0 * tiles_hw;
+        const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        const int h0 = th_i * L::TH, w0 = tw_i * L::TW;
+        mbar_wait(empty + s, ph ^ 1);
+        uint8_t* sx = smem + s * L::STAGE_BYTES;
+        mbar_expect_tx(full + s, (uint32_t)(L::ROWS * 128 + L::G_BYTES));
+        tma_load_5d(sx, &tmX, full + s, c0, w0 - p.pad_w, h0 - p.pad_h, d0 - p.pad_d, n);
+        tma_load_5d(sx + L::X_BYTES, &tmG, full + s, n0, w0, h0, d0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_tf32(128, BN, 1, 1);   // both operands MN-major
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % L::STAGES;
+        const uint32_t ph = (it / L::STAGES) & 1;
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t sx = smem_u32(smem + s * L::STAGE_BYTES);
+        // column groups of the x operand one voxel (128 bytes) apart; 4-voxel K groups 512 bytes apart
+        const uint64_t ad0 = smem_desc(sx, 128, 512, LAYOUT_SW128_BASE32B);
+        const uint64_t bd0 = smem_desc(sx + L::X_BYTES, 128, 512, LAYOUT_SW128_BASE32B);
+#pragma unroll
+        for (int a = 0; a < L::ACCS; ++a) {
+          const int kd = a / L::KH, kh = a % L::KH;
+#pragma unroll
+          for (int hy = 0; hy < L::TH; ++hy) {
+#pragma unroll
+            for (int ks = 0; ks < L::TW / UMMA_K; ++ks) {
+              const int row_x = (kd * L::HH + kh + hy) * L::HW + UMMA_K * ks;     // first voxel of this K slice, tap kw = 0
+              const int row_g = hy * L::TW + UMMA_K * ks;
+              umma_tf32(tmem_base + (uint32_t)(a * BN), ad0 + (uint64_t)(8 * row_x), bd0 + (uint64_t)(8 * row_g), idesc,
+                        (uint32_t)((it | hy | ks) != 0));
+            }
+          }
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // epilogue: TMEM lane = kw * 32 + (input channel - c0); BN output-channel columns per accumulator
+    const int kw = warp & 3;
+    const int ci = c0 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const bool live = kw < L::KW && ci < p.Cin;
+    const bool vec = (p.Cout & 3) == 0;
+#pragma unroll 1
+    for (int a = 0; a < L::ACCS; ++a) {
+      float* dst = dw + ((long long)(a * L::KW + kw) * p.Cin + ci) * p.Cout + n0;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 16) {
+        float v[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(kw * 32) << 16) + (uint32_t)(a * BN + cc), v);
+        if (!live || n0 + cc >= p.Cout) continue;
+        if (vec && n0 + cc + 16 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) red_add_v4(dst + cc + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + cc + j < p.Cout) atomicAdd(dst + cc + j, v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
+}
+
 // db[c] += sum over voxels of dy[voxel][c]  (dy channels-last, contiguous voxels x C; C <= 256).
 // thread = (channel, voxel lane); 4 independent accumulators keep 4 loads in flight per thread.
 __global__ void __launch_bounds__(256)
@@ -215,12 +363,23 @@ inline int pick_x_is_m(int Cin, int Cout) {
   return cx <= cg;
 }
 
+// The halo variant covers 3x3 / 3x3x3 stride-1 layers; it pays off while the per-tap kernel would pad most of
+// its 128-row operand (few input channels) and the output channels fit one or two 32-column tiles.
+bool wgrad_halo_fits(const dfmir_conv_desc* d) {
+  static const int off = getenv("DFMIR_WGRAD_HALO") ? atoi(getenv("DFMIR_WGRAD_HALO")) == 0 : 0;
+  if (off) return false;
+  for (int a = 0; a < d->nd; ++a) if (d->kernel[a] != 3 || d->pad[a] < 0 || d->pad[a] > 2) return false;
+  return d->Cin <= 128 && d->Cout <= 64 && d->out_shape[d->nd - 1] >= 24;
+}
+
 int wgrad_supported(const dfmir_conv_desc* d) {
   if (!d || (d->nd != 2 && d->nd != 3) || d->stride != 1) return 0;
-  if (d->Cin % 4 || d->Cout % 4 || d->Cin < 16 || d->Cout < 16) return 0;   // rows of both operands: 16-byte multiples
+  if (d->Cin % 4 || d->Cout % 4 || d->Cin < 4 || d->Cout < 4) return 0;     // rows of both operands: 16-byte multiples
   const int nd = d->nd;
   if (d->x_strides[nd + 1] != 1 || d->y_strides[nd + 1] != 1) return 0;
   for (int i = 0; i <= nd; ++i) if ((d->x_strides[i] & 3) || (d->y_strides[i] & 3)) return 0;
+  // the per-tap kernel pads the M side to 128 channels: below 16 channels only the halo variant is worth running
+  if ((d->Cin < 16 || d->Cout < 16) && !wgrad_halo_fits(d)) return 0;
   return 1;
 }
 
@@ -253,6 +412,50 @@ int encode_map5(CUtensorMap* tm, const float* act, const long long* st, int nd, 
   return DFMIR_OK;
 }
 
+int bias_grad(const float* dy, float* db, const dfmir_conv_desc* d, cudaStream_t st, const char* who) {
+  const int nd = d->nd;
+  long long pixels = d->N, dense = d->Cout;
+  bool contiguous = d->y_strides[nd + 1] == 1;
+  for (int a = nd - 1; a >= 0; --a) { contiguous = contiguous && d->y_strides[1 + a] == dense; dense *= d->out_shape[a]; pixels *= d->out_shape[a]; }
+  contiguous = contiguous && d->y_strides[0] == dense;
+  DFMIR_CHECK_ARG(contiguous, "%s: bias gradient needs a contiguous dy", who);
+  DFMIR_CHECK_ARG(d->Cout <= 256, "%s: bias gradient covers Cout <= 256", who);
+  int blocks = 16 * dfmir_num_sms();
+  long long per_block = (pixels + blocks - 1) / blocks;
+  if (per_block < 32) per_block = 32;
+  blocks = (int)((pixels + per_block - 1) / per_block);
+  bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, pixels, d->Cout, per_block);
+  DFMIR_CHECK_LAUNCH(who);
+  return DFMIR_OK;
+}
+
+template <int BN, int KD>
+int launch_wgrad_halo(const float* x, const float* dy, float* dw, const dfmir_conv_desc* d, cudaStream_t st, const char* who) {
+  using L = WgHalo<BN, KD>;
+  const int nd = d->nd;
+  WgHaloP p;
+  p.N = d->N; p.D = nd == 3 ? d->out_shape[0] : 1; p.H = d->out_shape[nd - 2]; p.W = d->out_shape[nd - 1];
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.pad_d = nd == 3 ? d->pad[0] : 0; p.pad_h = d->pad[nd - 2]; p.pad_w = d->pad[nd - 1];
+  p.tiles_h = (p.H + L::TH - 1) / L::TH; p.tiles_w = (p.W + L::TW - 1) / L::TW;
+  p.ntiles = p.N * p.D * p.tiles_h * p.tiles_w;
+  if (p.ntiles == 0) return DFMIR_OK;
+  const int chunks = (d->Cin + 31) / 32, n_tiles = (d->Cout + BN - 1) / BN;
+  int S = dfmir_num_sms() / (chunks * n_tiles);
+  if (S < 1) S = 1;
+  if (S > p.ntiles) S = p.ntiles;
+  CUtensorMap tmX, tmG;
+  int rc = encode_map5(&tmX, x, d->x_strides, nd, d->Cin, d->in_shape, d->N, L::HW, L::HH, L::HD, who);
+  if (rc) return rc;
+  rc = encode_map5(&tmG, dy, d->y_strides, nd, d->Cout, d->out_shape, d->N, L::TW, L::TH, 1, who);
+  if (rc) return rc;
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<BN, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  dim3 grid((unsigned)S, (unsigned)chunks, (unsigned)n_tiles);
+  conv_wgrad_halo_kernel<BN, KD><<<grid, 192, L::TOTAL, st>>>(tmX, tmG, dw, p);
+  DFMIR_CHECK_LAUNCH(who);
+  return DFMIR_OK;
+}
+
 }  // namespace
 
 extern "C" int dfmir_conv_umma_wgrad_supported(const dfmir_conv_desc* d) { return wgrad_supported(d); }
@@ -263,13 +466,20 @@ extern "C" int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw,
                                      void* stream) {
   const char* who = "dfmir_conv_umma_wgrad";
   if (!wgrad_supported(d)) {
-    dfmir_set_error("%s: needs a 2-D / 3-D stride-1 convolution with channel counts that are multiples of 4 and >= 16 on "
+    dfmir_set_error("%s: needs a 2-D / 3-D stride-1 convolution with channel counts that are multiples of 4 (>= 16 unless 3x3 / 3x3x3) on "
                     "channels-last operands with 16-byte aligned strides", who);
     return DFMIR_ERR_UNSUPPORTED;
   }
   DFMIR_CHECK_ARG(x && dy && dw, "%s: null pointer", who);
   cudaStream_t st = (cudaStream_t)stream;
   const int nd = d->nd;
+  if (wgrad_halo_fits(d)) {
+    int rc;
+    if (nd == 3) rc = d->Cout <= 16 ? launch_wgrad_halo<16, 3>(x, dy, dw, d, st, who) : launch_wgrad_halo<32, 3>(x, dy, dw, d, st, who);
+    else rc = d->Cout <= 16 ? launch_wgrad_halo<16, 1>(x, dy, dw, d, st, who) : launch_wgrad_halo<32, 1>(x, dy, dw, d, st, who);
+    if (rc) return rc;
+    return db ? bias_grad(dy, db, d, st, who) : DFMIR_OK;
+  }
   WgradP p;
   p.N = d->N; p.D = nd == 3 ? d->out_shape[0] : 1; p.H = d->out_shape[nd - 2]; p.W = d->out_shape[nd - 1];
   p.Cin = d->Cin; p.Cout = d->Cout;
@@ -305,19 +515,6 @@ extern "C" int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw,
   else if (BN == 64) rc = launch_wgrad<64>(tmX, tmG, dw, p, taps, S, st);
   else rc = launch_wgrad<32>(tmX, tmG, dw, p, taps, S, st);
   if (rc) return rc;
-  if (db) {
-    long long pixels = d->N, dense = d->Cout;
-    bool contiguous = d->y_strides[nd + 1] == 1;
-    for (int a = nd - 1; a >= 0; --a) { contiguous = contiguous && d->y_strides[1 + a] == dense; dense *= d->out_shape[a]; pixels *= d->out_shape[a]; }
-    contiguous = contiguous && d->y_strides[0] == dense;
-    DFMIR_CHECK_ARG(contiguous, "%s: bias gradient needs a contiguous dy", who);
-    DFMIR_CHECK_ARG(d->Cout <= 256, "%s: bias gradient covers Cout <= 256", who);
-    int blocks = 16 * dfmir_num_sms();
-    long long per_block = (pixels + blocks - 1) / blocks;
-    if (per_block < 32) per_block = 32;
-    blocks = (int)((pixels + per_block - 1) / per_block);
-    bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, pixels, d->Cout, per_block);
-    DFMIR_CHECK_LAUNCH(who);
-  }
+  if (db) return bias_grad(dy, db, d, st, who);
   return DFMIR_OK;
 }

@@ -167,6 +167,10 @@ class _ConvFn(torch.autograd.Function):
         tc = CONV_ENGINE != "simt" and N * math.prod(O) >= UMMA_MIN_POSITIONS and Cin != 1 and Cout != 1
         if tc:
             from . import umma
+        if tc and planar_out and Cout % 4 and stride == 1 and Cin % 4 == 0 and x.data_ptr() % 16 == 0:
+            # planar flow head (2 or 3 output channels): its gradient as a channels-last copy padded to 4 channels,
+            # so that both backward products run on the tensor-core kernels (TMA rows must be 16-byte multiples)
+            return _ConvFn._backward_padded_head(ctx, x, w, dy)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
@@ -184,6 +188,34 @@ class _ConvFn(torch.autograd.Function):
             else:
                 _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops)
         return dx, dw, db, None, None, None, None, None
+
+
+def _backward_padded_head(ctx, x, w, dy):
+    from . import umma
+    nd, N, Cin, Cout, S, O, kernel, pad, stride, act, planar_out, has_bias, engine, flops = ctx.meta
+    Cp = (Cout + 3) // 4 * 4
+    dyp = torch.zeros((N, *O, Cp), dtype=dy.dtype, device=dy.device)
+    dyp[..., :Cout] = dy.movedim(1, -1)
+    ysp = _cl_strides(dyp, nd)
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+        dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
+        d = _make_desc(nd, N, Cin, Cp, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ysp)
+        wp = torch.nn.functional.pad(w, (0, Cp - Cout))          # (taps, Cin, Cp): K-major rows of 16 bytes
+        if umma.supported(d, True):
+            umma.conv_dgrad(dyp, wp, dx, d, flops)
+        else:
+            _run(lambda: _lib.call("dfmir_conv_dgrad", dyp, wp.transpose(1, 2).contiguous(), dx, ctypes.byref(d)), flops)
+    if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+        dwp = torch.zeros((w.shape[0], Cin, Cp), dtype=w.dtype, device=w.device)
+        d = _make_desc(nd, N, Cin, Cp, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(x, nd), ysp)
+        umma.conv_wgrad(x, dyp, dwp, None, d, flops)
+        dw = dwp[..., :Cout].contiguous()
+        db = dy.sum(dim=[0] + list(range(2, nd + 2))) if has_bias else None
+    return dx, dw, db, None, None, None, None, None
+
+
+_ConvFn._backward_padded_head = staticmethod(_backward_padded_head)
 
 
 def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False):

@@ -178,6 +178,12 @@ CASES3D = [  # N, Cin, Cout, D, H, W
     (2, 48, 32, 8, 16, 16),
     (1, 16, 3, 12, 20, 24),          # 3-D flow head, partial tiles in every axis
     (1, 64, 32, 16, 16, 16),
+    # weight gradient through the halo kernel (all taps per CTA, W >= 24): partial tiles in h and w, 1-3 channel chunks
+    (1, 36, 32, 6, 10, 40),
+    (1, 16, 16, 5, 7, 70),
+    (2, 48, 32, 4, 9, 33),
+    (1, 32, 64, 4, 8, 32),           # two output-channel tiles
+    (1, 96, 16, 3, 6, 24),
 ]
 
 
@@ -229,6 +235,46 @@ def test_umma_conv3d_fwd_dgrad(case):
         np.testing.assert_allclose(wg.grad.cpu().numpy(), w.grad.numpy(), atol=3e-3 * wscale)
     else:
         np.testing.assert_allclose(wg.grad.cpu().numpy(), w.grad.numpy(), atol=2e-4 * wscale)
+    np.testing.assert_allclose(bg.grad.cpu().numpy(), b.grad.numpy(), atol=2e-4 * float(b.grad.abs().max()))
+
+
+@pytest.mark.parametrize("shape,Cin,Cout", [((64, 64), 16, 2), ((12, 20, 40), 16, 3), ((6, 10, 72), 32, 3)])
+def test_planar_flow_head_backward_on_tensor_cores(shape, Cin, Cout):
+    """The VoxelMorph flow head (vxm/networks.py:1076-1081) writes its 2 / 3 channels planar for the warp kernels; its
+    backward runs on the tcgen05 kernels through a channels-last copy of the gradient padded to 4 channels."""
+    from oracle import torch_port as tp
+    import dfmir_b200.functional as Fn
+    nd = len(shape)
+    conv = F.conv2d if nd == 2 else F.conv3d
+    r = gi.rng(990 + Cin + Cout + nd)
+    x = torch.from_numpy(r.standard_normal((2, Cin, *shape)).astype(np.float32)).requires_grad_()
+    w = torch.from_numpy((r.standard_normal((Cout, Cin, *([3] * nd))) / np.sqrt(Cin * 3 ** nd)).astype(np.float32)).requires_grad_()
+    b = torch.from_numpy(r.standard_normal(Cout).astype(np.float32)).requires_grad_()
+    y = conv(x, w, b, padding=1)
+    gy = torch.from_numpy(r.standard_normal(tuple(y.shape)).astype(np.float32))
+    y.backward(gy)
+    xq, wq, gq = (tp.tf32_round(t.detach()).double() for t in (x, w, gy))
+    grad_in = torch.nn.grad.conv2d_input if nd == 2 else torch.nn.grad.conv3d_input
+    grad_w = torch.nn.grad.conv2d_weight if nd == 2 else torch.nn.grad.conv3d_weight
+    emu_dx, emu_dw = grad_in(x.shape, wq, gq, padding=1), grad_w(xq, w.shape, gq, padding=1)
+    prev = Fn.CONV_ENGINE
+    Fn.CONV_ENGINE = "auto"
+    prof = Fn.ConvProfile(); Fn.PROFILE = prof
+    try:
+        xg = x.detach().cuda().movedim(1, -1).contiguous().requires_grad_()
+        wg, bg = w.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+        yg = Fn.conv_cl(xg, wg, bg, pad=1, planar_out=True)
+        assert yg.shape == y.shape
+        yg.backward(gy.cuda())
+        torch.cuda.synchronize()
+    finally:
+        Fn.CONV_ENGINE, Fn.PROFILE = prev, None
+    kinds = prof.by_kind()
+    assert "umma_dgrad" in kinds and "umma_wgrad" in kinds, kinds.keys()
+    for name, got, want, em in (("dgrad", xg.grad.movedim(-1, 1).cpu(), x.grad, emu_dx), ("wgrad", wg.grad.cpu(), w.grad, emu_dw)):
+        scale = float(want.abs().max())
+        assert float((got - want).abs().max()) <= 3e-3 * scale, name
+        assert float((got.double() - em).abs().max()) <= 3e-5 * scale, (name, "vs TF32-truncated float64 reference")
     np.testing.assert_allclose(bg.grad.cpu().numpy(), b.grad.numpy(), atol=2e-4 * float(b.grad.abs().max()))
 
 

@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""Per-kernel time breakdown (torch.profiler) of the 3-D bench step (VoxelMorph-3D 128^3, batch 2)."""
+"""Per-kernel time breakdown (torch.profiler) of the 3-D bench step.
+    python tools/breakdown3d.py                      # VoxelMorph-3D 128^3, batch 2, 6-level features (configs[2])
+    python tools/breakdown3d.py 160,192,160 1 default  # configs[3]"""
 import collections, os, sys
 import torch
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
 from dfmir_b200 import vxm
 from torch.profiler import profile, ProfilerActivity
-B, S = 2, 128
+shape = tuple(int(v) for v in sys.argv[1].split(",")) if len(sys.argv) > 1 else (128, 128, 128)
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+feats = None if len(sys.argv) > 3 and sys.argv[3] == "default" else [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]]
 torch.manual_seed(0)
-net = vxm.VxmDense((S, S, S), [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]], int_steps=7, bidir=False).cuda()
+net = vxm.VxmDense(shape, feats, int_steps=7, bidir=False).cuda()
 opt = torch.optim.Adam(net.parameters(), lr=2e-4)
-A = torch.rand(B, 1, S, S, S, device="cuda"); Bm = torch.rand(B, 1, S, S, S, device="cuda")
+A = torch.rand(B, 1, *shape, device="cuda"); Bm = torch.rand(B, 1, *shape, device="cuda")
 def step():
     opt.zero_grad()
     y, f, n, g = net.forward_with_losses(A, Bm)
