@@ -481,6 +481,221 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2), 3x3, 256-channel tiles
+// The single-CTA kernels above are bound by the shared-memory operand reads of the MMA (a TF32 128 x 128 x 8 MMA reads
+// 8 KB for 64 cycles of math, a 128 x 256 x 8 one 12 KB for 128: 59 % / 75 % tensor-pipe activity measured).  Here
+// two CTAs of a cluster (two SMs of a TPC) run ONE 256 x 256 x 8 MMA per K slice: each SM holds its own 128-voxel
+// halo tile (the A half) and HALF of the weight tile (128 of the 256 output channels); the tensor cores of both SMs
+// read A locally and B from both shared memories, so every SM reads 8 KB per 128 cycles of math and streams half
+// the weight bytes from L2.  Structure as conv_umma_halo_kernel (16 x 8 voxel tile per CTA, TMEM double buffering):
+//   * both CTAs issue their own TMA loads (cta_group::2 form: the transaction bytes are signalled on the LEADER's
+//     barrier, whose expect_tx covers both halves);
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 and commits with a multicast arrive, which frees the
+//     stage in both CTAs and hands the accumulators (each CTA's own 128 TMEM lanes) to both epilogues;
+//   * the epilogue warps of both CTAs release the accumulator stage on the leader's barrier (remote arrive).
+constexpr int PAIR_BST = 8;                // weight stages of 16 KB (128 channels x 32 tf32)
+constexpr int PAIR_B_BYTES = 128 * 128;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the same barrier in the leader CTA (rank 0) of the pair, as a shared::cluster address
+__device__ __forceinline__ uint32_t leader_addr(const void* local) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(0));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs once all MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const float* __restrict__ bias, float* __restrict__ y, const HaloP hp) {
+  constexpr int BN = 256, AS = 2, BST = PAIR_BST;
+  constexpr int HH = 18, HW = 10;                  // 16 x 8 voxel tile + halo of a 3 x 3 kernel
+  const UmmaP& p = hp.u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                              // 2 activation stages
+  uint8_t* sB = smem + 2 * hp.a_bytes;             // BST weight stages (this CTA's 128 output channels)
+  uint64_t* a_full = (uint64_t*)(sB + BST * PAIR_B_BYTES);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* b_full = a_empty + 2;
+  uint64_t* b_empty = b_full + BST;
+  uint64_t* tmem_full = b_empty + BST;
+  uint64_t* tmem_empty = tmem_full + AS;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + AS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int tiles_hw = p.tiles_h * p.tiles_w;
+  const int pairs = (p.ptiles + 1) / 2;            // ptiles = 16 x 8 voxel tiles; CTA `rank` of a pair takes tile 2 * pair + rank
+  const int items = pairs * n_tiles;
+  const int cchunks = (p.Cin + KCH - 1) / KCH;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int s = 0; s < 2; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < BST; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int a = 0; a < AS; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                                  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs): own halo tile, own half of the weight tile
+      uint32_t ia = 0;
+      int sb = 0; uint32_t bph = 0;
+      const uint32_t a_bytes_box = (uint32_t)(HH * HW * 128);
+      for (int item = cluster_id; item < items; item += nclusters) {
+        const int nt = item % n_tiles, pt = 2 * (item / n_tiles) + (int)rank;
+        const int n = pt / tiles_hw; const int rem = pt - n * tiles_hw;      // pt >= ptiles: n >= N, the box is zero-filled
+        const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        const int h0 = th_i * 16, w0 = tw_i * 8;
+        for (int cc = 0; cc < cchunks; ++cc, ++ia) {
+          const int sa = ia & 1;
+          mbar_wait(a_empty + sa, ((ia >> 1) & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(a_full + sa, 2 * a_bytes_box);
+          tma_load_5d_pair(sA + sa * hp.a_bytes, &tmA, leader_addr(a_full + sa), cc * KCH, w0 - p.pad_w, h0 - p.pad_h, 0, n);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(b_empty + sb, bph ^ 1);
+            if (rank == 0) mbar_expect_tx(b_full + sb, 2 * PAIR_B_BYTES);
+            tma_load_3d_pair(sB + sb * PAIR_B_BYTES, &tmB, leader_addr(b_full + sb), cc * KCH, nt * BN + (int)rank * 128, p.flip ? 8 - tap : tap);
+            if (++sb == BST) { sb = 0; bph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------- MMA issuer (leader CTA only): M = 256 (128 voxels of each CTA), N = 256
+      constexpr uint32_t idesc = instr_desc_tf32(256, BN);
+      const uint64_t bdesc0 = smem_desc_sw128(smem_u32(sB), 16, 1024);
+      int sb = 0; uint32_t bph = 0;
+      uint32_t ia = 0, ti = 0;
+      for (int item = cluster_id; item < items; item += nclusters, ++ti) {
+        const uint32_t as = ti % AS, aph = (ti / AS) & 1;
+        mbar_wait(tmem_empty + as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * BN;
+        for (int cc = 0; cc < cchunks; ++cc, ++ia) {
+          const int sa = ia & 1;
+          mbar_wait(a_full + sa, (ia >> 1) & 1);
+          tc_fence_after();
+          const uint64_t adesc0 = smem_desc_sw128(smem_u32(sA + sa * hp.a_bytes), 16, HW * 128);
+          static_for<0, 9>([&](auto tap_c) {
+            constexpr int tap = decltype(tap_c)::value;
+            constexpr int row = (tap / 3) * HW + tap % 3;
+            mbar_wait(b_full + sb, bph);
+            tc_fence_after();
+            const uint64_t bdesc = bdesc0 + (uint64_t)(sb * (PAIR_B_BYTES / 16));
+            const uint64_t adesc = adesc0 + (uint64_t)(8 * row);
+#pragma unroll
+            for (int k = 0; k < KCH / UMMA_K; ++k)
+              umma_tf32_pair(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (tap | k) != 0 ? 1u : (uint32_t)(cc != 0));
+            umma_commit_pair(b_empty + sb);
+            if (++sb == BST) { sb = 0; bph ^= 1; }
+          });
+          umma_commit_pair(a_empty + sa);
+        }
+        umma_commit_pair(tmem_full + as);
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): warp e reads TMEM lanes 32 * (e % 4) .. + 31, columns 128 * (e / 4) .. + 127
+    const int e = warp - 2;
+    const int quarter = warp & 3;
+    const int chalf = e >> 2;
+    const int row = quarter * 32 + lane;
+    const int th = row >> 3, tw = row & 7;
+    const bool vec_ok = p.ys[4] == 1 && (p.Cout & 3) == 0;
+    uint32_t ti = 0;
+    for (int item = cluster_id; item < items; item += nclusters, ++ti) {
+      const uint32_t as = ti % AS, aph = (ti / AS) & 1;
+      const int nt = item % n_tiles, pt = 2 * (item / n_tiles) + (int)rank;
+      const int n0 = nt * BN;
+      const int n = pt / tiles_hw; const int rem = pt - n * tiles_hw;
+      const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+      mbar_wait(tmem_full + as, aph);
+      tc_fence_after();
+      const int oh = th_i * 16 + th, ow = tw_i * 8 + tw;
+      const bool valid = n < p.N && oh < p.H && ow < p.W;
+      float* yp = y + (long long)n * p.ys[0] + (long long)oh * p.ys[2] + (long long)ow * p.ys[3];
+      const uint32_t acc = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(acc + (uint32_t)c0, v);
+        if (valid && n0 + c0 < p.Cout) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = v[i];
+            if (bias && n0 + c0 + i < p.Cout) t += __ldg(bias + n0 + c0 + i);
+            v[i] = act_apply(t, p.act);
+          }
+          if (vec_ok && n0 + c0 + 32 <= p.Cout) {
+            float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + c0 + i < p.Cout) yp[(long long)(n0 + c0 + i) * p.ys[4]] = v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_addr(tmem_empty + as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                                  // the leader's MMAs read the peer's shared memory until the end
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512u);
+}
+
 // ---------------------------------------------------------------- host side
 // strides arrive as {n, spatial[nd], c}
 struct Strides5 { long long n, d, h, w, c; };
@@ -614,6 +829,49 @@ int launch_halo(const float* act, const Strides5& as, int ID, int IH, int IW, co
   return launch_halo_k<BN, SD, SH, SW, BST, 0>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
 }
 
+// CTA-pair kernel: 2-D 3 x 3 convolutions with Cout a multiple of 256 (the ResnetBlock convs, forward and data gradient)
+int launch_pair(const float* act, const Strides5& as, int IH, int IW, const float* w, const float* bias, float* y, UmmaP p,
+                cudaStream_t st, const char* who) {
+  HaloP hp;
+  hp.HD = 1; hp.HH = 18; hp.HW = 10;
+  hp.a_bytes = (hp.HH * hp.HW * 128 + 1023) / 1024 * 1024;
+  const int nbars = 4 + 2 * PAIR_BST + 4;
+  const size_t smem = 2 * (size_t)hp.a_bytes + (size_t)PAIR_BST * PAIR_B_BYTES + nbars * 8 + 16 + 1024;
+  p.tiles_d = 1; p.tiles_h = (p.H + 15) / 16; p.tiles_w = (p.W + 7) / 8;
+  p.ptiles = p.N * p.tiles_h * p.tiles_w;
+  hp.u = p;
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)IW, (cuuint64_t)IH, 1, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)as.w * 4, (cuuint64_t)as.h * 4, (cuuint64_t)as.h * IH * 4, (cuuint64_t)as.n * 4};
+    cuuint32_t box[5] = {KCH, (cuuint32_t)hp.HW, (cuuint32_t)hp.HH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(halo tile) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
+    cuuint32_t box[3] = {KCH, 128, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  }
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int items = ((p.ptiles + 1) / 2) * ((p.Cout + 255) / 256);
+  if (items == 0) return DFMIR_OK;
+  int clusters = dfmir_num_sms() / 2;
+  if (clusters > items) clusters = items;
+  const int rounds = (items + clusters - 1) / clusters;
+  clusters = (items + rounds - 1) / rounds;
+  conv_umma_pair_kernel<<<2 * clusters, THREADS, smem, st>>>(tmA, tmB, bias, y, hp);
+  DFMIR_CHECK_LAUNCH(who);
+  return DFMIR_OK;
+}
+
 // act: source activation (channels-last, c stride 1) with element strides `as` and spatial size (ID, IH, IW)
 int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const float* w, const float* bias, float* y,
              const UmmaP& p, cudaStream_t st, const char* who) {
@@ -629,6 +887,9 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   const double eff8 = (double)p.H * p.W / ((double)((p.H + 15) / 16 * 16) * ((p.W + 7) / 8 * 8));
   const bool narrow256 = p.Cout == 256 && ID == 1 && p.KD * p.KH * p.KW > 1 && eff16 < 0.72 && eff8 > eff16 * 1.08 && cfg == 0;
   if (narrow256) BN = 256;
+  static const int pair = getenv("DFMIR_UMMA_PAIR") ? atoi(getenv("DFMIR_UMMA_PAIR")) : 1;
+  if (pair && ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.Cout % 256 == 0 && p.Cin % KCH == 0 && !p.per_sample && p.ys[4] == 1)
+    return launch_pair(act, as, IH, IW, w, bias, y, p, st, who);
   CUtensorMap tmA, tmB;
   {
     const long long sd = ID > 1 ? as.d : as.h * IH;      // 2-D: a depth axis of extent 1 (its stride is never used)
