@@ -493,8 +493,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 //   * the leader's MMA thread issues tcgen05.mma.cta_group::2 and commits with a multicast arrive, which frees the
 //     stage in both CTAs and hands the accumulators (each CTA's own 128 TMEM lanes) to both epilogues;
 //   * the epilogue warps of both CTAs release the accumulator stage on the leader's barrier (remote arrive).
-constexpr int PAIR_BST = 8;                // weight stages of 16 KB (128 channels x 32 tf32)
-constexpr int PAIR_B_BYTES = 128 * 128;
+constexpr int PAIR_BST = 8;                // weight stages: this CTA's BN / 2 output channels x 32 tf32 (16 KB at BN = 256)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync() {
@@ -541,10 +540,12 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t base, uint32_t cols) 
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
 }
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const float* __restrict__ bias, float* __restrict__ y, const HaloP hp) {
-  constexpr int BN = 256, AS = 2, BST = PAIR_BST;
+  constexpr int AS = 2, BST = PAIR_BST;
+  constexpr int PAIR_B_BYTES = (BN / 2) * 128;
   constexpr int HH = 18, HW = 10;                  // 16 x 8 voxel tile + halo of a 3 x 3 kernel
   const UmmaP& p = hp.u;
   extern __shared__ uint8_t smem_raw[];
@@ -601,7 +602,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(b_empty + sb, bph ^ 1);
             if (rank == 0) mbar_expect_tx(b_full + sb, 2 * PAIR_B_BYTES);
-            tma_load_3d_pair(sB + sb * PAIR_B_BYTES, &tmB, leader_addr(b_full + sb), cc * KCH, nt * BN + (int)rank * 128, p.flip ? 8 - tap : tap);
+            tma_load_3d_pair(sB + sb * PAIR_B_BYTES, &tmB, leader_addr(b_full + sb), cc * KCH, nt * BN + (int)rank * (BN / 2), p.flip ? 8 - tap : tap);
             if (++sb == BST) { sb = 0; bph ^= 1; }
           }
         }
@@ -643,7 +644,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    // ---------------- epilogue (both CTAs): warp e reads TMEM lanes 32 * (e % 4) .. + 31, columns 128 * (e / 4) .. + 127
+    // ---------------- epilogue (both CTAs): warp e reads TMEM lanes 32 * (e % 4) .. + 31, columns (BN / 2) * (e / 4) .. + BN / 2 - 1
     const int e = warp - 2;
     const int quarter = warp & 3;
     const int chalf = e >> 2;
@@ -664,7 +665,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       float* yp = y + (long long)n * p.ys[0] + (long long)oh * p.ys[2] + (long long)ow * p.ys[3];
       const uint32_t acc = tmem_base + as * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         float v[32];
         tmem_ld_32x32(acc + (uint32_t)c0, v);
         if (valid && n0 + c0 < p.Cout) {
@@ -829,13 +830,16 @@ int launch_halo(const float* act, const Strides5& as, int ID, int IH, int IW, co
   return launch_halo_k<BN, SD, SH, SW, BST, 0>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
 }
 
-// CTA-pair kernel: 2-D 3 x 3 convolutions with Cout a multiple of 256 (the ResnetBlock convs, forward and data gradient)
+// CTA-pair kernel: 2-D 3 x 3 convolutions with Cout a multiple of BN = 256 or 128 (ResnetBlock and down / up-sampling
+// convs of the generator, forward and data gradient)
+template <int BN>
 int launch_pair(const float* act, const Strides5& as, int IH, int IW, const float* w, const float* bias, float* y, UmmaP p,
                 cudaStream_t st, const char* who) {
   HaloP hp;
   hp.HD = 1; hp.HH = 18; hp.HW = 10;
   hp.a_bytes = (hp.HH * hp.HW * 128 + 1023) / 1024 * 1024;
   const int nbars = 4 + 2 * PAIR_BST + 4;
+  constexpr int PAIR_B_BYTES = (BN / 2) * 128;
   const size_t smem = 2 * (size_t)hp.a_bytes + (size_t)PAIR_BST * PAIR_B_BYTES + nbars * 8 + 16 + 1024;
   p.tiles_d = 1; p.tiles_h = (p.H + 15) / 16; p.tiles_w = (p.W + 7) / 8;
   p.ptiles = p.N * p.tiles_h * p.tiles_w;
@@ -854,20 +858,20 @@ int launch_pair(const float* act, const Strides5& as, int IH, int IW, const floa
   {
     cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 9};
     cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
-    cuuint32_t box[3] = {KCH, 128, 1};
+    cuuint32_t box[3] = {KCH, BN / 2, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
   }
-  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int items = ((p.ptiles + 1) / 2) * ((p.Cout + 255) / 256);
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int items = ((p.ptiles + 1) / 2) * ((p.Cout + BN - 1) / BN);
   if (items == 0) return DFMIR_OK;
   int clusters = dfmir_num_sms() / 2;
   if (clusters > items) clusters = items;
   const int rounds = (items + clusters - 1) / clusters;
   clusters = (items + rounds - 1) / rounds;
-  conv_umma_pair_kernel<<<2 * clusters, THREADS, smem, st>>>(tmA, tmB, bias, y, hp);
+  conv_umma_pair_kernel<BN><<<2 * clusters, THREADS, smem, st>>>(tmA, tmB, bias, y, hp);
   DFMIR_CHECK_LAUNCH(who);
   return DFMIR_OK;
 }
@@ -888,8 +892,10 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   const bool narrow256 = p.Cout == 256 && ID == 1 && p.KD * p.KH * p.KW > 1 && eff16 < 0.72 && eff8 > eff16 * 1.08 && cfg == 0;
   if (narrow256) BN = 256;
   static const int pair = getenv("DFMIR_UMMA_PAIR") ? atoi(getenv("DFMIR_UMMA_PAIR")) : 1;
-  if (pair && ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.Cout % 256 == 0 && p.Cin % KCH == 0 && !p.per_sample && p.ys[4] == 1)
-    return launch_pair(act, as, IH, IW, w, bias, y, p, st, who);
+  if (pair && ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.Cin % KCH == 0 && !p.per_sample && p.ys[4] == 1) {
+    if (p.Cout % 256 == 0) return launch_pair<256>(act, as, IH, IW, w, bias, y, p, st, who);
+    if (p.Cout % 128 == 0 && pair > 1) return launch_pair<128>(act, as, IH, IW, w, bias, y, p, st, who);
+  }
   CUtensorMap tmA, tmB;
   {
     const long long sd = ID > 1 ? as.d : as.h * IH;      // 2-D: a depth axis of extent 1 (its stride is never used)

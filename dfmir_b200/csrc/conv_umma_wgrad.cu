@@ -175,6 +175,145 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2) of the per-tap kernel
+// The 256 x 256-channel weight gradient above is bound by L2 -> shared-memory traffic: each of the two M tiles of
+// a tap re-reads the whole dy chunk (48 KB per 512 cycles of MMA per SM, 12.5 TB/s over the chip).  Here the two
+// M tiles of a tap form a CTA pair that runs ONE 256 x 256 x 8 MMA per K slice: CTA r stages x channels
+// [128 r, 128 r + 128) (its half of M) and dy channels [128 r, 128 r + 128) (its half of N), 32 KB per stage
+// instead of 48, and the accumulator rows of its x channels stay in its own TMEM.  Barrier protocol as in
+// conv_umma_pair_kernel (conv_umma.cu): TMA bytes of both CTAs are counted on the leader's barrier, the leader
+// issues the MMAs and commits with a multicast arrive.  grid = (2 * taps, M pairs, S), cluster (2, 1, 1).
+constexpr int WP_STAGES = 6;
+constexpr int WP_STAGE_BYTES = 8 * CHUNK_BYTES;     // 4 x-channel groups + 4 dy-channel groups of 32
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t leader_addr(const void* local) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(0));
+  return r;
+}
+__device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
+conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                       float* __restrict__ dw, const WgradP p) {
+  constexpr int STAGES = WP_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + STAGES * WP_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int tap = blockIdx.x >> 1;
+  const int split = blockIdx.z, S = gridDim.z;
+  const int q = tap % p.KW; const int t2 = tap / p.KW;
+  const int r = t2 % p.KH, kd = t2 / p.KH;
+  const int dd = kd - p.pad_d, dh = r - p.pad_h, dwv = q - p.pad_w;
+  const int m0 = blockIdx.y * 256 + (int)rank * 128;          // this CTA's x channels (rows of its accumulator)
+  const int nh = (int)rank * 128;                             // this CTA's half of the 256 dy channels
+  const int iters = (p.nchunks - split + S - 1) / S;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmG);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int tiles_hw = p.tiles_h * p.tiles_w;
+      const int tiles_img = p.tiles_d * tiles_hw;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const int c = split + it * S;
+        const int n = c / tiles_img; int rem = c - n * tiles_img;
+        const int td_i = rem / tiles_hw; rem -= td_i * tiles_hw;
+        const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        const int d0 = td_i * p.TD, h0 = th_i * p.TH, w0 = tw_i * p.TW;
+        mbar_wait(empty + s, ph ^ 1);
+        uint8_t* sa = smem + s * WP_STAGE_BYTES;
+        uint8_t* sb = sa + 4 * CHUNK_BYTES;
+        if (rank == 0) mbar_expect_tx(full + s, 2u * WP_STAGE_BYTES);
+        const uint32_t bar = leader_addr(full + s);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tma_load_5d_pair(sa + g * CHUNK_BYTES, &tmX, bar, m0 + g * 32, w0 + dwv, h0 + dh, d0 + dd, n);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tma_load_5d_pair(sb + g * CHUNK_BYTES, &tmG, bar, nh + g * 32, w0, h0, d0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = instr_desc_tf32(256, 256, 1, 1);   // both operands MN-major
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full + s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * WP_STAGE_BYTES);
+        const uint64_t adesc = smem_desc(sa, CHUNK_BYTES, 512, LAYOUT_SW128_BASE32B);
+        const uint64_t bdesc = smem_desc(sa + 4 * CHUNK_BYTES, CHUNK_BYTES, 512, LAYOUT_SW128_BASE32B);
+#pragma unroll
+        for (int k = 0; k < PIX / UMMA_K; ++k)
+          umma_tf32_pair(tmem_base, adesc + (uint64_t)(64 * k), bdesc + (uint64_t)(64 * k), idesc, (uint32_t)((it | k) != 0));
+        umma_commit_pair(empty + s);
+      }
+      umma_commit_pair(tmem_full);
+    }
+  } else {
+    // epilogue (both CTAs): thread = accumulator row = x channel m0 + row; 256 dy-channel columns
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* dst = dw + ((long long)tap * p.Cin + m0 + row) * p.Cout;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red_add_v4(dst + c0 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
 // ---------------------------------------------------------------- halo variant (few-channel 3x3 / 3x3x3 layers)
 // The per-tap kernel above re-reads x and dy once per tap (27 times in 3-D) and pads the M side to 128
 // channels: right for the 256-channel ResnetBlock convs, 5 ms per launch for VoxelMorph-3D's full-resolution
@@ -510,7 +649,18 @@ extern "C" int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw,
   if (rc) return rc;
   rc = encode_map5(&tmG, dy, d->y_strides, nd, d->Cout, d->out_shape, d->N, p.TW, p.TH, p.TD, who);
   if (rc) return rc;
-  if (BN == 256) rc = launch_wgrad<256>(tmX, tmG, dw, p, taps, S, st);
+  static const int pair = getenv("DFMIR_WGRAD_PAIR") ? atoi(getenv("DFMIR_WGRAD_PAIR")) : 1;
+  if (pair && p.x_is_m && d->Cout == 256 && d->Cin % 256 == 0) {
+    const int smem = WP_STAGES * WP_STAGE_BYTES + (2 * WP_STAGES + 1) * 8 + 16 + 1024;
+    DFMIR_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int Sp = dfmir_num_sms() / (2 * taps * (d->Cin / 256));
+    if (Sp < 1) Sp = 1;
+    if (Sp > p.nchunks) Sp = p.nchunks;
+    dim3 grid((unsigned)(2 * taps), (unsigned)(d->Cin / 256), (unsigned)Sp);
+    conv_wgrad_pair_kernel<<<grid, 192, smem, st>>>(tmX, tmG, dw, p);
+    DFMIR_CHECK_LAUNCH(who);
+    rc = DFMIR_OK;
+  } else if (BN == 256) rc = launch_wgrad<256>(tmX, tmG, dw, p, taps, S, st);
   else if (BN == 128) rc = launch_wgrad<128>(tmX, tmG, dw, p, taps, S, st);
   else if (BN == 64) rc = launch_wgrad<64>(tmX, tmG, dw, p, taps, S, st);
   else rc = launch_wgrad<32>(tmX, tmG, dw, p, taps, S, st);
