@@ -335,9 +335,12 @@ struct WgHalo {
   static constexpr int HW = TW + 3, HH = TH + KH - 1, HD = KD;
   static constexpr int ROWS = HW * HH * HD;
   static constexpr int X_BYTES = (ROWS * 128 + 1023) / 1024 * 1024;
-  static constexpr int G_BYTES = TH * TW * 128;
+  static constexpr int GA = (BN + 31) / 32;                 // 32-channel column groups of the dy operand
+  static constexpr int GA_BYTES = TH * TW * 128;
+  static constexpr int G_BYTES = GA * GA_BYTES;
   static constexpr int STAGE_BYTES = X_BYTES + G_BYTES;
-  static constexpr int STAGES = KD == 3 ? 2 : 4;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+  static_assert(STAGES >= 2, "two stages must fit");
   static constexpr int ACCS = KD * KH;
   static constexpr int COLS = ACCS * BN;
   static constexpr uint32_t TMEM_COLS = COLS <= 32 ? 32 : (COLS <= 64 ? 64 : (COLS <= 128 ? 128 : (COLS <= 256 ? 256 : 512)));
@@ -397,7 +400,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         uint8_t* sx = smem + s * L::STAGE_BYTES;
         mbar_expect_tx(full + s, (uint32_t)(L::ROWS * 128 + L::G_BYTES));
         tma_load_5d(sx, &tmX, full + s, c0, w0 - p.pad_w, h0 - p.pad_h, d0 - p.pad_d, n);
-        tma_load_5d(sx + L::X_BYTES, &tmG, full + s, n0, w0, h0, d0, n);
+#pragma unroll
+        for (int g = 0; g < L::GA; ++g) tma_load_5d(sx + L::X_BYTES + g * L::GA_BYTES, &tmG, full + s, n0 + 32 * g, w0, h0, d0, n);
       }
     }
   } else if (warp == 1) {
@@ -411,7 +415,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const uint32_t sx = smem_u32(smem + s * L::STAGE_BYTES);
         // column groups of the x operand one voxel (128 bytes) apart; 4-voxel K groups 512 bytes apart
         const uint64_t ad0 = smem_desc(sx, 128, 512, LAYOUT_SW128_BASE32B);
-        const uint64_t bd0 = smem_desc(sx + L::X_BYTES, 128, 512, LAYOUT_SW128_BASE32B);
+        const uint64_t bd0 = smem_desc(sx + L::X_BYTES, L::GA_BYTES, 512, LAYOUT_SW128_BASE32B);     // dy column groups GA_BYTES apart
 #pragma unroll
         for (int a = 0; a < L::ACCS; ++a) {
           const int kd = a / L::KH, kh = a % L::KH;
@@ -508,7 +512,8 @@ bool wgrad_halo_fits(const dfmir_conv_desc* d) {
   static const int off = getenv("DFMIR_WGRAD_HALO") ? atoi(getenv("DFMIR_WGRAD_HALO")) == 0 : 0;
   if (off) return false;
   for (int a = 0; a < d->nd; ++a) if (d->kernel[a] != 3 || d->pad[a] < 0 || d->pad[a] > 2) return false;
-  return d->Cin <= 128 && d->Cout <= 64 && d->out_shape[d->nd - 1] >= 24;
+  // output channels per CTA: 9 accumulators x 32 columns in 3-D (two tiles up to 64), 3 x 128 in 2-D
+  return d->Cin <= 128 && d->Cout <= (d->nd == 3 ? 64 : 128) && d->out_shape[d->nd - 1] >= 24;
 }
 
 int wgrad_supported(const dfmir_conv_desc* d) {
@@ -615,7 +620,10 @@ extern "C" int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw,
   if (wgrad_halo_fits(d)) {
     int rc;
     if (nd == 3) rc = d->Cout <= 16 ? launch_wgrad_halo<16, 3>(x, dy, dw, d, st, who) : launch_wgrad_halo<32, 3>(x, dy, dw, d, st, who);
-    else rc = d->Cout <= 16 ? launch_wgrad_halo<16, 1>(x, dy, dw, d, st, who) : launch_wgrad_halo<32, 1>(x, dy, dw, d, st, who);
+    else if (d->Cout <= 16) rc = launch_wgrad_halo<16, 1>(x, dy, dw, d, st, who);
+    else if (d->Cout <= 32) rc = launch_wgrad_halo<32, 1>(x, dy, dw, d, st, who);
+    else if (d->Cout <= 64) rc = launch_wgrad_halo<64, 1>(x, dy, dw, d, st, who);
+    else rc = launch_wgrad_halo<128, 1>(x, dy, dw, d, st, who);
     if (rc) return rc;
     return db ? bias_grad(dy, db, d, st, who) : DFMIR_OK;
   }
