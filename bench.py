@@ -243,7 +243,7 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * B * S * S * 4), "d2h_bytes_per_step": 6 * 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM convolution, forward + data gradient)",
+        "roofline": {"bound": "tensor", "kernel": "conv_umma_pair_kernel / conv_umma_halo_kernel / conv_umma_kernel (tcgen05 implicit-GEMM convolution, forward + data gradient)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": f"bf16_tflops_sustained, {pk_src}; kind::tf32 issues at half the bf16 rate, so the "
                                     "TF32 ceiling of this kernel is peak/2",
