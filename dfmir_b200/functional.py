@@ -5,6 +5,7 @@ tape; every forward and backward below is a C-ABI call into hand-written sm_100a
 Internal activation layout is channels-last: (N, *spatial, C) contiguous fp32.
 """
 import ctypes
+import weakref
 import math
 import os
 
@@ -218,18 +219,56 @@ def _backward_padded_head(ctx, x, w, dy):
 _ConvFn._backward_padded_head = staticmethod(_backward_padded_head)
 
 
+class _PackFn(torch.autograd.Function):
+    """(Cout, Cin, *k) parameter -> kernel layout (taps, Cin + pad, Cout); pad = zero rows for zero-padded activation
+    channels (upsample_concat_cl(pad_channels_to=4))."""
+
+    @staticmethod
+    def forward(ctx, weight, pad_cin):
+        Cout, Cin = weight.shape[:2]
+        w = weight.reshape(Cout, Cin, -1).permute(2, 1, 0)
+        if pad_cin > 0:
+            w = torch.nn.functional.pad(w, (0, 0, 0, pad_cin))
+        ctx.meta = (tuple(weight.shape), Cin, id(weight))
+        return w.contiguous()
+
+    @staticmethod
+    def backward(ctx, dw):
+        shape, Cin, key = ctx.meta
+        _pack_cache.pop(key, None)          # the tape that used this copy is done: re-pack on the next forward
+        return dw[:, :Cin, :].permute(2, 1, 0).reshape(shape), None
+
+
+_pack_cache = {}
+
+
+def packed_weight(weight, pad_cin=0):
+    """Kernel-layout copy of a convolution weight, shared by every use of the same (unmodified) parameter inside one
+    autograd tape: the generator's weights are used by four passes per step, which then cost one re-layout and one
+    gradient accumulation instead of four."""
+    grad = torch.is_grad_enabled() and weight.requires_grad
+    key = id(weight)
+    hit = _pack_cache.get(key)
+    if hit is not None:
+        ref, version, pad, g, w = hit
+        if ref() is weight and version == weight._version and pad == pad_cin and g == grad:
+            return w
+    if len(_pack_cache) > 256:              # views (linear()) and replaced parameters leave dead entries behind
+        for k in [k for k, v in _pack_cache.items() if v[0]() is None]:
+            del _pack_cache[k]
+    w = _PackFn.apply(weight, pad_cin)
+    _pack_cache[key] = (weakref.ref(weight), weight._version, pad_cin, grad, w)
+    return w
+
+
 def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False):
     """Convolution on a channels-last activation with a PyTorch-layout weight (Cout, Cin, *k).
     Returns (N,*O,Cout), or the planar (N,Cout,*O) when planar_out."""
     nd = weight.dim() - 2
     kernel = list(weight.shape[2:])
     pads = [pad] * nd if isinstance(pad, int) else list(pad)
-    Cout, Cin = weight.shape[:2]
-    # (Cout,Cin,*k) -> (taps, Cin, Cout); tiny tensors, torch autograd carries the permutation back
-    w = weight.reshape(Cout, Cin, -1).permute(2, 1, 0)
-    if x.shape[-1] > Cin:       # activation with zero padding channels (upsample_concat_cl(pad_channels_to=4))
-        w = torch.nn.functional.pad(w, (0, 0, 0, x.shape[-1] - Cin))
-    w = w.contiguous()
+    Cin = weight.shape[1]
+    w = packed_weight(weight, x.shape[-1] - Cin)
     return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out)
 
 

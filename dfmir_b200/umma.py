@@ -2,6 +2,7 @@
 (csrc/conv_umma.cu) and the calls into libdfmir_b200.so for them.  Everything else, and the weight
 gradient for now, runs on the fp32 CUDA-core path (csrc/conv_simt.cu)."""
 import ctypes
+import weakref
 
 from . import _lib
 
@@ -20,8 +21,26 @@ def _run(fn, flops, kind):
     Fn._run(fn, flops, kind)
 
 
+_kmajor_cache = {}
+
+
+def _kmajor(w):
+    """[tap][Cout][Cin] copy (K-major rows for the B operand) of a packed weight; cached per packed tensor, which
+    functional.packed_weight shares between the passes of a step."""
+    key = id(w)
+    hit = _kmajor_cache.get(key)
+    if hit is not None and hit[0]() is w and hit[1] == w._version:
+        return hit[2]
+    if len(_kmajor_cache) > 256:
+        for k in [k for k, v in _kmajor_cache.items() if v[0]() is None]:
+            del _kmajor_cache[k]
+    wk = w.detach().transpose(1, 2).contiguous()
+    _kmajor_cache[key] = (weakref.ref(w), w._version, wk)
+    return wk
+
+
 def conv_fwd(x, w, bias, y, d, flops=0.0):
-    wk = w.transpose(1, 2).contiguous()          # [tap][Cout][Cin]: K-major rows for the B operand
+    wk = _kmajor(w)
     _run(lambda: _lib.call("dfmir_conv_umma_fwd", x, wk, bias, y, ctypes.byref(d)), flops, "umma_fwd")
 
 
