@@ -158,7 +158,8 @@ def run_ours(args):
     from dfmir_b200 import functional as Fn
 
     B, S = args.batch, args.size
-    opt = rm.default_options(batch_size=B, crop_size=S, load_size=S, gpu_ids=[local])
+    use_graph = os.environ.get("DFMIR_CUDA_GRAPH", "1") != "0"
+    opt = rm.default_options(batch_size=B, crop_size=S, load_size=S, gpu_ids=[local], cuda_graph=use_graph)
     torch.manual_seed(1234)
     with contextlib.redirect_stdout(sys.stderr):
         model = rm.REGISTRATIONModel(opt)
@@ -202,11 +203,26 @@ def run_ours(args):
     # untimed, for a fixed number of further steps (~1 s) so that the K timed steps below measure the steady state
     for _ in range(EXTRA_WARMUP_2D):            # a fixed count: every rank must run the same number of all-reduces
         step_resident()
+    # the whole step (forward, losses, backward, gradient all-reduce, Adam) as one CUDA graph: same kernels, no
+    # per-launch host work (DFMIR_CUDA_GRAPH=0: eager launches)
+    graphed, graph_note = False, None
+    if use_graph:
+        try:
+            model.capture_step()
+            graphed = True
+        except Exception as exc:                 # stay on the eager launches of the same kernels
+            model._graph = None
+            graph_note = f"capture failed, eager launches: {type(exc).__name__}: {str(exc)[:200]}"
+            print("bench.py: " + graph_note, file=sys.stderr)
+            torch.cuda.synchronize()
+        for _ in range(3):
+            step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.launch_count_reset()
     ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count()
+    launches = model.graph_launches_per_step * args.steps if graphed else _lib.launch_count()
     ms_e2e = timed(step_e2e, args.steps)
+    model._graph = None                          # the per-kernel event pass below needs eager launches
     # per-kernel durations for the roofline: the same K steps once more with a CUDA-event pair around every convolution
     # launch (kept out of the timed regions above: ~1000 event records per step cost host time the step no longer hides)
     prof = Fn.ConvProfile()
@@ -246,7 +262,8 @@ def run_ours(args):
                    "schedule": "feat_k of real_A / real_B tapped from the full generator pass (identical values; the reference "
                                "recomputes them with 3 more encoder passes) - DFMIR_REUSE_REAL_FEATURES=0 restores that",
                    "l2_policy": "inputs larger than L2: each step streams > 10 GB of activations (L2 is 126 MB)",
-                   "warmup_note": f"{args.warmup} + {EXTRA_WARMUP_2D} untimed steps before the timed region"},
+                   "warmup_note": f"{args.warmup} + {EXTRA_WARMUP_2D} untimed steps before the timed region",
+                   "cuda_graph": graphed, **({"cuda_graph_note": graph_note} if graph_note else {})},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * B * S * S * 4), "d2h_bytes_per_step": 6 * 4},

@@ -879,21 +879,20 @@ int launch_pair(const float* act, const Strides5& as, int IH, int IW, const floa
 // act: source activation (channels-last, c stride 1) with element strides `as` and spatial size (ID, IH, IW)
 int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const float* w, const float* bias, float* y,
              const UmmaP& p, cudaStream_t st, const char* who) {
-  static const int cfg = getenv("DFMIR_UMMA_CFG") ? atoi(getenv("DFMIR_UMMA_CFG")) : 0;   // tuning experiments
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
   if (((uintptr_t)act & 15) || ((uintptr_t)w & 15)) { dfmir_set_error("%s: TMA needs 16-byte aligned base pointers", who); return DFMIR_ERR_ARG; }
   int BN = p.Cout <= 16 ? 16 : (p.Cout <= 32 ? 32 : (p.Cout <= 64 ? 64 : 128));
-  if (p.Cout == 256 && (cfg == 1 || cfg == 5 || cfg == 6 || cfg == 7 || cfg == 8)) BN = 256;
   // 16x16-voxel CTA tiles waste a third of the work on a 66x66 output (the data gradient of the ResnetBlock
   // convs): there, 16x8 tiles with all 256 channels per CTA measured 542 vs 441 TFLOP/s (batch 32)
   const double eff16 = (double)p.H * p.W / ((double)((p.H + 15) / 16 * 16) * ((p.W + 15) / 16 * 16));
   const double eff8 = (double)p.H * p.W / ((double)((p.H + 15) / 16 * 16) * ((p.W + 7) / 8 * 8));
-  const bool narrow256 = p.Cout == 256 && ID == 1 && p.KD * p.KH * p.KW > 1 && eff16 < 0.72 && eff8 > eff16 * 1.08 && cfg == 0;
+  const bool narrow256 = p.Cout == 256 && ID == 1 && p.KD * p.KH * p.KW > 1 && eff16 < 0.72 && eff8 > eff16 * 1.08;
   if (narrow256) BN = 256;
   static const int pair = getenv("DFMIR_UMMA_PAIR") ? atoi(getenv("DFMIR_UMMA_PAIR")) : 1;
   if (pair && ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.Cin % KCH == 0 && !p.per_sample && p.ys[4] == 1) {
     if (p.Cout % 256 == 0) return launch_pair<256>(act, as, IH, IW, w, bias, y, p, st, who);
+    // DFMIR_UMMA_PAIR=2 also pairs the 128-channel layers: measured slower than the single-CTA 2 x 128 tiles (5.7 vs 5.2 ms / step)
     if (p.Cout % 128 == 0 && pair > 1) return launch_pair<128>(act, as, IH, IW, w, bias, y, p, st, who);
   }
   CUtensorMap tmA, tmB;
@@ -923,16 +922,6 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
     int rc = launch_halo<256, 1, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
     if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
   }
-  if (halo && p.KD * p.KH * p.KW > 1 && BN == 256 && ID == 1 && cfg == 8) {
-    int rc = launch_halo<256, 1, 1, 2, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-    if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
-  }
-  if (halo && p.KD * p.KH * p.KW > 1 && BN == 256 && ID == 1 && (cfg == 6 || cfg == 7)) {
-    // experiment: 256-wide tiles (operand reads 96 B/clk instead of 128) on the halo pipeline, no epilogue overlap
-    int rc = cfg == 6 ? launch_halo<256, 1, 1, 2, 3>(act, as, ID, IH, IW, tmB, bias, y, p, st, who)
-                      : launch_halo<256, 1, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-    if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
-  }
   if (halo && p.KD * p.KH * p.KW > 1 && BN <= 128) {
     int rc = DFMIR_ERR_UNSUPPORTED;
     if (ID > 1) {
@@ -948,14 +937,11 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
     }
     if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
   }
-  // 128-channel tiles x 2 sub-tiles: 48 KB stages x 4 and double-buffered accumulators beat one 256-wide tile
-  // (64 KB x 3, no epilogue overlap): 552 vs 430 TFLOP/s on the ResnetBlock conv at batch 32
-  if (BN == 256) return cfg == 1 ? launch_umma<256, 1, 4, 2>(tmA, tmB, bias, y, p, st, who) : launch_umma<256, 2, 3, 1>(tmA, tmB, bias, y, p, st, who);
-  if (BN == 128) {
-    if (cfg == 3) return launch_umma<128, 4, 2, 1>(tmA, tmB, bias, y, p, st, who);
-    if (cfg == 4) return launch_umma<128, 1, 6, 2>(tmA, tmB, bias, y, p, st, who);
-    return launch_umma<128, 2, 4, 2>(tmA, tmB, bias, y, p, st, who);
-  }
+  // plain variant (1x1 kernels, DFMIR_UMMA_HALO=0).  128-channel tiles x 2 sub-tiles: 48 KB stages x 4 and
+  // double-buffered accumulators beat one 256-wide tile (64 KB x 3, no epilogue overlap): 552 vs 430 TFLOP/s on the
+  // ResnetBlock conv at batch 32
+  if (BN == 256) return launch_umma<256, 2, 3, 1>(tmA, tmB, bias, y, p, st, who);
+  if (BN == 128) return launch_umma<128, 2, 4, 2>(tmA, tmB, bias, y, p, st, who);
   if (BN == 64) return launch_umma<64, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
   if (BN == 32) return launch_umma<32, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);
   return launch_umma<16, 4, 3, 2>(tmA, tmB, bias, y, p, st, who);

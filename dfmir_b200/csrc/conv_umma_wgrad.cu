@@ -466,10 +466,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
-// db[c] += sum over voxels of dy[voxel][c]  (dy channels-last, contiguous voxels x C; C <= 256).
+// db[c] += sum over voxels of dy[voxel][c]  (dy channels-last, voxel stride Cs; this launch covers C <= 256 channels).
 // thread = (channel, voxel lane); 4 independent accumulators keep 4 loads in flight per thread.
 __global__ void __launch_bounds__(256)
-bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, long long pixels, int C, long long per_block) {
+bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, long long pixels, int C, int Cs, long long per_block) {
   __shared__ float part[256];
   const int t = threadIdx.x;
   const int lanes = 256 / C;
@@ -480,12 +480,12 @@ bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, long long
   if (pl < lanes) {
     long long px = p0 + pl;
     for (; px + 3LL * lanes < p1; px += 4LL * lanes) {
-      a0 += __ldg(dy + px * C + c);
-      a1 += __ldg(dy + (px + lanes) * C + c);
-      a2 += __ldg(dy + (px + 2LL * lanes) * C + c);
-      a3 += __ldg(dy + (px + 3LL * lanes) * C + c);
+      a0 += __ldg(dy + px * Cs + c);
+      a1 += __ldg(dy + (px + lanes) * Cs + c);
+      a2 += __ldg(dy + (px + 2LL * lanes) * Cs + c);
+      a3 += __ldg(dy + (px + 3LL * lanes) * Cs + c);
     }
-    for (; px < p1; px += lanes) a0 += __ldg(dy + px * C + c);
+    for (; px < p1; px += lanes) a0 += __ldg(dy + px * Cs + c);
   }
   float acc = (a0 + a1) + (a2 + a3);
   part[t] = acc;
@@ -563,13 +563,15 @@ int bias_grad(const float* dy, float* db, const dfmir_conv_desc* d, cudaStream_t
   for (int a = nd - 1; a >= 0; --a) { contiguous = contiguous && d->y_strides[1 + a] == dense; dense *= d->out_shape[a]; pixels *= d->out_shape[a]; }
   contiguous = contiguous && d->y_strides[0] == dense;
   DFMIR_CHECK_ARG(contiguous, "%s: bias gradient needs a contiguous dy", who);
-  DFMIR_CHECK_ARG(d->Cout <= 256, "%s: bias gradient covers Cout <= 256", who);
   int blocks = 16 * dfmir_num_sms();
   long long per_block = (pixels + blocks - 1) / blocks;
   if (per_block < 32) per_block = 32;
   blocks = (int)((pixels + per_block - 1) / per_block);
-  bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, pixels, d->Cout, per_block);
-  DFMIR_CHECK_LAUNCH(who);
+  for (int c0 = 0; c0 < d->Cout; c0 += 256) {      // 256 channels per launch
+    const int C = d->Cout - c0 < 256 ? d->Cout - c0 : 256;
+    bias_grad_kernel<<<blocks, 256, 0, st>>>(dy + c0, db + c0, pixels, C, d->Cout, per_block);
+    DFMIR_CHECK_LAUNCH(who);
+  }
   return DFMIR_OK;
 }
 

@@ -41,7 +41,7 @@ def default_options(**overrides):
         lr_decay_iters=50, continue_train=False, epoch='latest', verbose=False, pretrained_name=None,
         CUT_mode='CUT', lambda_GAN=0.0, lambda_NCE=0.25, nce_idt=True, nce_layers='0,4,8,12,16',
         nce_includes_all_negatives_from_minibatch=False, netF='mlp_sample', netF_nc=256, nce_T=0.07,
-        num_patches=256, flip_equivariance=False, gan_mode='lsgan', pool_size=0)
+        num_patches=256, flip_equivariance=False, gan_mode='lsgan', pool_size=0, cuda_graph=False)
     for k, v in overrides.items():
         setattr(opt, k, v)
     return opt
@@ -105,6 +105,8 @@ class BaseModel:
         self.metric = 0
         self._flat_grad = None
         self._world = 1
+        self._graph = None
+        self.graph_launches_per_step = 0
 
     def setup(self, opt):
         if self.isTrain:
@@ -169,6 +171,7 @@ class BaseModel:
         return self.image_paths
 
     def update_learning_rate(self):
+        self._graph = None          # a captured step has the old learning rate baked in
         for scheduler in self.schedulers:
             if self.opt.lr_policy == 'plateau':
                 scheduler.step(self.metric)
@@ -236,8 +239,9 @@ class REGISTRATIONModel(BaseModel):
         if self.isTrain:
             self.criterionNCE = [PatchNCELoss(opt).to(self.device) for _ in self.nce_layers]
             self.criterionNCC = losses.NCC_Loss(self.device, name='ncc', kernel_var=[9, 9], kernel_type='mean')
-            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2))
-            self.optimizer_R = torch.optim.Adam(self.netR.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2))
+            cap = bool(getattr(opt, 'cuda_graph', False))        # step counters on the device, so that Adam can be graph-captured
+            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2), capturable=cap)
+            self.optimizer_R = torch.optim.Adam(self.netR.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2), capturable=cap)
             self.optimizers.append(self.optimizer_G)
             self.optimizers.append(self.optimizer_R)
 
@@ -251,16 +255,65 @@ class REGISTRATIONModel(BaseModel):
             self.compute_G_loss().backward()
             if self.opt.lambda_NCE > 0.0:
                 self.optimizer_F = torch.optim.Adam(self.netF.parameters(), lr=self.opt.lr,
-                                                    betas=(self.opt.beta1, self.opt.beta2))
+                                                    betas=(self.opt.beta1, self.opt.beta2),
+                                                    capturable=bool(getattr(self.opt, 'cuda_graph', False)))
                 self.optimizers.append(self.optimizer_F)
 
     def optimize_parameters(self):
+        if self._graph is not None:
+            self._graph.replay()
+            return
+        self._step()
+
+    def capture_step(self):
+        """Capture one training step (forward, losses, backward, gradient all-reduce, the three Adam steps) into a CUDA
+        graph; optimize_parameters() then replays it: ~2.3 k kernel launches per step stop costing host time
+        (SURVEY 8f N1).  Needs opt.cuda_graph=True at construction (capturable Adam), a few eager steps on inputs of
+        the final shape first (lazy initialisation, allocator warm-up), and set_input() afterwards copies into the
+        captured input buffers.  update_learning_rate() drops the graph (the learning rate is baked into it); call
+        capture_step() again after it."""
+        if not getattr(self.opt, 'cuda_graph', False):
+            raise _lib.DfmirError("capture_step: construct the model with opt.cuda_graph=True (capturable Adam)")
+        self._graph = None
+        self._static_A, self._static_B = self.real_A.clone(), self.real_B.clone()
+        self.real_A, self.real_B = self._static_A, self._static_B
+        # AccumulateGrad nodes made by earlier steps live on the default stream for as long as any tensor of those
+        # steps' tapes is alive, and would tie the capture to the legacy stream: drop the old tapes, warm up on a side
+        # stream (torch.cuda.graphs recipe), drop again, then capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        self._release_tapes()
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        self._release_tapes()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self._step()
+        self.graph_launches_per_step = _lib.launch_count() - n0
+        self._graph = graph
+
+    def _release_tapes(self):
+        import gc
+        from . import functional as Fn
+        for k, v in list(vars(self).items()):
+            if torch.is_tensor(v) and v.grad_fn is not None:
+                setattr(self, k, v.detach())
+        Fn._pack_cache.clear()
+        gc.collect()
+
+    def _step(self):
         self.forward()
         y_output = self.netR(self.real_A, self.real_B)
         pos_flow = y_output[2]
         self.registered = self.spatialTransformer(self.fake_B, pos_flow)
         self.regA = y_output[0]
-        test_image = open_image_to_torch("./deform256.jpg", self.opt.crop_size).to(self.device, non_blocking=True)
+        test_image = getattr(self, '_test_image_dev', None)
+        if test_image is None:      # decoded and uploaded once (the reference re-reads the file every step, :148)
+            test_image = self._test_image_dev = open_image_to_torch("./deform256.jpg", self.opt.crop_size).to(self.device)
         with torch.no_grad():
             self.dvf = self.spatialTransformer(test_image.expand(pos_flow.shape[0], -1, -1, -1).contiguous()
                                                if pos_flow.shape[0] > 1 else test_image, pos_flow)
@@ -289,8 +342,13 @@ class REGISTRATIONModel(BaseModel):
 
     def set_input(self, input):
         AtoB = self.opt.direction == 'AtoB'
-        self.real_A = input['A' if AtoB else 'B'].to(self.device, non_blocking=True)
-        self.real_B = input['B' if AtoB else 'A'].to(self.device, non_blocking=True)
+        if self._graph is not None:         # the captured step reads these buffers
+            self._static_A.copy_(input['A' if AtoB else 'B'], non_blocking=True)
+            self._static_B.copy_(input['B' if AtoB else 'A'], non_blocking=True)
+            self.real_A, self.real_B = self._static_A, self._static_B
+        else:
+            self.real_A = input['A' if AtoB else 'B'].to(self.device, non_blocking=True)
+            self.real_B = input['B' if AtoB else 'A'].to(self.device, non_blocking=True)
         self.image_paths = input.get('A_paths' if AtoB else 'B_paths', [])
 
     def forward(self):

@@ -35,6 +35,8 @@ CASES = [  # N, Cin, Cout, H, W, k, pad   (H, W = input spatial size)
     (2, 48, 32, 64, 64, 3, 1),       # uparm.5: partial second chunk, N tile 32
     (2, 16, 2, 64, 64, 3, 1),        # flow head: half a chunk of K, two output channels in a 16-wide tile
     (1, 96, 32, 64, 72, 3, 1),       # three chunks, partial tiles in w
+    (1, 64, 512, 12, 20, 3, 1),      # CTA-pair kernel with two 256-channel N tiles, partial tiles in h and w
+    (3, 32, 256, 10, 12, 3, 1),      # CTA pairs across samples (2 tiles per image), one K chunk
 ]
 
 
