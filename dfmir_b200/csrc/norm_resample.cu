@@ -319,13 +319,17 @@ in_bwd_reduce_v4_kernel(const float4* __restrict__ dy, const float4* __restrict_
 }
 
 // grid (chunks, N); thread = (channel quad, pixel lane), statistics hoisted out of the pixel loop
+// bsum (nullable): per-CTA sums of the result over the CTA's pixels, [chunk][n][C] floats - the bias gradient of the
+// convolution that produced x (its dy IS this dx), finished by in_bias_finalize_kernel.
 __global__ void __launch_bounds__(256)
 in_bwd_apply_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ stats, const double* __restrict__ sums,
-                       float4* __restrict__ dx, int HW, int C4, int chunk) {
+                       float4* __restrict__ dx, float* __restrict__ bsum, int HW, int C4, int chunk) {
+  __shared__ float bred[256][4];
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
   const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, npl = 256 / C4;
-  if (pl >= npl) return;
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pl < npl) {
   const float4 s0 = __ldg(stats + ((long long)n * C4 + c4) * 2), s1 = __ldg(stats + ((long long)n * C4 + c4) * 2 + 1);
   const double* sm = sums + ((long long)n * C4 * 4 + c4 * 4) * 2;
   const double inv = 1.0 / HW;
@@ -355,7 +359,42 @@ in_bwd_apply_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ 
         r[j] = rstd[j] * (gs[j] - m1[j] - xh * m2[j]);
       }
       gb[(long long)(pp + k * npl) * C4] = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bs[j] += r[j];
     }
+  }
+  }
+  if (bsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bred[threadIdx.x][j] = bs[j];
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < npl; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bs[j] += bred[l * C4 + c4][j];
+    float* o = bsum + ((long long)blockIdx.x * gridDim.y + n) * C4 * 4 + c4 * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = bs[j];
+  }
+}
+
+// db[c] += sum over the (chunk, sample) rows of the per-CTA sums.  grid (C / 32, row splits); thread = (channel of a
+// 32-channel group, one of 8 row lanes): coalesced 128-byte reads, shared-memory sum of the lanes, one atomic per
+// channel and block (db zero-filled by the caller).
+__global__ void __launch_bounds__(256)
+in_bias_finalize_kernel(const float* __restrict__ bsum, float* __restrict__ db, int rows, int C) {
+  __shared__ float red[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float acc = 0.f;
+  if (c < C)
+    for (int r = blockIdx.y * 8 + rl; r < rows; r += 8 * gridDim.y) acc += bsum[(long long)r * C + c];
+  red[rl][cl] = acc;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int l = 1; l < 8; ++l) acc += red[l][cl];
+    atomicAdd(db + c, acc);
   }
 }
 
@@ -665,6 +704,12 @@ extern "C" int dfmir_instnorm_fwd(const float* x, const float* res, float* y, fl
 extern "C" int dfmir_instnorm_bwd(const float* dy, const float* x, const float* stats, float* dx, float* dres,
                                   void* ws, size_t ws_bytes, int N, int H, int W, int C, int relu, int out_pad,
                                   int res_pad, void* stream) {
+  return dfmir_instnorm_bwd_bias(dy, x, stats, dx, dres, nullptr, ws, ws_bytes, N, H, W, C, relu, out_pad, res_pad, stream);
+}
+
+extern "C" int dfmir_instnorm_bwd_bias(const float* dy, const float* x, const float* stats, float* dx, float* dres,
+                                       float* dbias, void* ws, size_t ws_bytes, int N, int H, int W, int C, int relu,
+                                       int out_pad, int res_pad, void* stream) {
   DFMIR_CHECK_ARG(dy && x && stats && dx && ws, "dfmir_instnorm_bwd: null pointer");
   DFMIR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0, "dfmir_instnorm_bwd: bad sizes");
   DFMIR_CHECK_ARG(ws_bytes >= dfmir_instnorm_workspace_bytes(N, C), "dfmir_instnorm_bwd: workspace too small");
@@ -682,10 +727,19 @@ extern "C" int dfmir_instnorm_bwd(const float* dy, const float* x, const float* 
     in_sum_partials_kernel<<<(2 * N * C + 255) / 256, 256, 0, st>>>(partials, sums, 2 * N * C, nch);
     DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(sum)");
     int ach; const int achunk = apply_chunk(H * W, N, &ach);
-    in_bwd_apply_v4_kernel<<<dim3(ach, N), 256, 0, st>>>((const float4*)x, (const float4*)stats, sums, (float4*)dx, H * W, C / 4, achunk);
+    // the reduction's partial sums are consumed: their space holds the per-CTA bias sums (ach * N * C floats)
+    float* bsum = dbias ? (float*)partials : nullptr;
+    in_bwd_apply_v4_kernel<<<dim3(ach, N), 256, 0, st>>>((const float4*)x, (const float4*)stats, sums, (float4*)dx, bsum, H * W, C / 4, achunk);
     DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(apply)");
+    if (dbias) {
+      DFMIR_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * C, st));
+      const int rows = ach * N;
+      in_bias_finalize_kernel<<<dim3((C + 31) / 32, rows >= 512 ? 16 : 1), 256, 0, st>>>(bsum, dbias, rows, C);
+      DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(bias)");
+    }
     return DFMIR_OK;
   }
+  DFMIR_CHECK_ARG(dbias == nullptr, "dfmir_instnorm_bwd_bias: the bias by-product needs the 128-bit path (C %% 4 == 0, 16-byte aligned tensors)");
   DFMIR_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)N * C, st));
   in_bwd_reduce_kernel<<<dim3(nch, N), 256, 0, st>>>(dy, x, stats, dx, dres, sums, H, W, C, relu, out_pad, res_pad, chunk);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_bwd(reduce)");

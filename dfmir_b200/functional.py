@@ -121,7 +121,8 @@ class _ConvFn(torch.autograd.Function):
     """y = act(conv(x, w) + b); x (N,*S,Cin) channels-last (any strides), w (taps,Cin,Cout)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, kernel, stride, pad, act, planar_out):
+    def forward(ctx, x, w, bias, kernel, stride, pad, act, planar_out, bias_slot=None):
+        ctx.bias_slot = bias_slot if act == ACT_NONE else None
         _lib.require_cuda(x, w)
         x, w = _f32(x), _f32(w).contiguous()
         nd = len(kernel)
@@ -171,7 +172,7 @@ class _ConvFn(torch.autograd.Function):
         if tc and planar_out and Cout % 4 and stride == 1 and Cin % 4 == 0 and x.data_ptr() % 16 == 0:
             # planar flow head (2 or 3 output channels): its gradient as a channels-last copy padded to 4 channels,
             # so that both backward products run on the tensor-core kernels (TMA rows must be 16-byte multiples)
-            return _ConvFn._backward_padded_head(ctx, x, w, dy)
+            return _ConvFn._backward_padded_head(ctx, x, w, dy) + (None,)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
@@ -183,12 +184,17 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             dw = torch.zeros_like(w)
             db = torch.zeros(Cout, dtype=w.dtype, device=w.device) if has_bias else None
+            slot, db_given = ctx.bias_slot, None
+            if slot is not None and slot.db is not None:        # summed by the InstanceNorm backward that produced dy
+                db_given, slot.db, db = slot.db, None, None
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(x, nd), ys)
             if tc and x.data_ptr() % 16 == 0 and dy.is_contiguous():
                 umma.conv_wgrad(x, dy, dw, db, d, flops)      # tcgen05 where the shape fits, else the fp32 kernel
             else:
                 _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops)
-        return dx, dw, db, None, None, None, None, None
+            if db_given is not None:
+                db = db_given if has_bias else None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 def _backward_padded_head(ctx, x, w, dy):
@@ -261,7 +267,19 @@ def packed_weight(weight, pad_cin=0):
     return w
 
 
-def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False):
+class BiasGradSlot:
+    """Hand-over of a convolution's bias gradient from the InstanceNorm that consumes its output: the IN backward
+    writes dx, which IS that convolution's output gradient, and sums it per channel on the way
+    (dfmir_instnorm_bwd_bias); the convolution's backward then skips its own pass over dx.  Pass the same slot to
+    conv_cl(..., bias_slot=) and instnorm_cl(..., bias_slot=); only valid when the IN is the ONLY consumer of the
+    convolution's output (no feature tap on it)."""
+    __slots__ = ("db",)
+
+    def __init__(self):
+        self.db = None
+
+
+def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False, bias_slot=None):
     """Convolution on a channels-last activation with a PyTorch-layout weight (Cout, Cin, *k).
     Returns (N,*O,Cout), or the planar (N,Cout,*O) when planar_out."""
     nd = weight.dim() - 2
@@ -269,12 +287,13 @@ def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False):
     pads = [pad] * nd if isinstance(pad, int) else list(pad)
     Cin = weight.shape[1]
     w = packed_weight(weight, x.shape[-1] - Cin)
-    return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out)
+    return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out, bias_slot)
 
 
 class _InstNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, relu, out_pad, res_pad, eps):
+    def forward(ctx, x, res, relu, out_pad, res_pad, eps, bias_slot=None):
+        ctx.bias_slot = bias_slot
         _lib.require_cuda(x)
         x = _f32(x).contiguous()
         N, H, W, C = x.shape
@@ -302,14 +321,20 @@ class _InstNormFn(torch.autograd.Function):
         if has_res and ctx.needs_input_grad[1]:
             dres = torch.empty((N, H + 2 * res_pad, W + 2 * res_pad, C), dtype=x.dtype, device=x.device)
         ws = workspace(_lib.lib().dfmir_instnorm_workspace_bytes(N, C), x.device)
-        _lib.call("dfmir_instnorm_bwd", dy, x, stats, dx, dres, ws, _lib.size_t(ws.numel()), N, H, W, C, relu,
+        slot = ctx.bias_slot
+        dbias = None
+        if slot is not None and C % 4 == 0 and dy.data_ptr() % 16 == 0:
+            dbias = torch.empty(C, dtype=x.dtype, device=x.device)
+        _lib.call("dfmir_instnorm_bwd_bias", dy, x, stats, dx, dres, dbias, ws, _lib.size_t(ws.numel()), N, H, W, C, relu,
                   out_pad, res_pad)
-        return dx, dres, None, None, None, None
+        if slot is not None:
+            slot.db = dbias
+        return dx, dres, None, None, None, None, None
 
 
-def instnorm_cl(x, relu=False, out_pad=0, res=None, res_pad=0, eps=1e-5):
+def instnorm_cl(x, relu=False, out_pad=0, res=None, res_pad=0, eps=1e-5, bias_slot=None):
     """InstanceNorm2d(affine=False) [+ReLU] [+res] written with a reflected halo of width out_pad."""
-    return _InstNormFn.apply(x, res, relu, out_pad, res_pad, eps)
+    return _InstNormFn.apply(x, res, relu, out_pad, res_pad, eps, bias_slot)
 
 
 class _PadReflectFn(torch.autograd.Function):

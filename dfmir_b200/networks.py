@@ -142,10 +142,11 @@ class ResnetBlock(nn.Module):
         """P: channels-last block input carrying a reflected halo of 1; returns x + conv_block(x)
         written with a halo of out_pad."""
         c1, c2 = self.conv_block[1], self.conv_block[5]
-        y = Fn.conv_cl(P, c1.weight, c1.bias)
-        P1 = Fn.instnorm_cl(y, relu=True, out_pad=1)
-        y = Fn.conv_cl(P1, c2.weight, c2.bias)
-        return Fn.instnorm_cl(y, relu=False, out_pad=out_pad, res=P, res_pad=1)
+        s1, s2 = Fn.BiasGradSlot(), Fn.BiasGradSlot()      # conv bias gradients summed by the IN backward passes
+        y = Fn.conv_cl(P, c1.weight, c1.bias, bias_slot=s1)
+        P1 = Fn.instnorm_cl(y, relu=True, out_pad=1, bias_slot=s1)
+        y = Fn.conv_cl(P1, c2.weight, c2.bias, bias_slot=s2)
+        return Fn.instnorm_cl(y, relu=False, out_pad=out_pad, res=P, res_pad=1, bias_slot=s2)
 
     def forward(self, x):
         P = Fn.pad_reflect_cl(x.permute(0, 2, 3, 1), 1)
@@ -220,12 +221,18 @@ class ResnetGenerator(nn.Module):
         try:
             x = input.permute(0, 2, 3, 1)
             P = Fn.pad_reflect_cl(x, 3); tap(0, P)
-            y = Fn.conv_cl(P, m[1].weight, m[1].bias); tap(1, y)
-            a = Fn.instnorm_cl(y, relu=True); tap(2, a); tap(3, a)
+            def slot(i):
+                """bias-gradient hand-over conv -> IN, unless the conv output is also a feature tap"""
+                return None if i in want else Fn.BiasGradSlot()
+
+            sl = slot(1)
+            y = Fn.conv_cl(P, m[1].weight, m[1].bias, bias_slot=sl); tap(1, y)
+            a = Fn.instnorm_cl(y, relu=True, bias_slot=sl); tap(2, a); tap(3, a)
             idx = 4
             for i in range(nd):
-                y = Fn.conv_cl(a, m[idx].weight, m[idx].bias, pad=1); tap(idx, y)
-                a = Fn.instnorm_cl(y, relu=True); tap(idx + 1, a); tap(idx + 2, a)
+                sl = slot(idx)
+                y = Fn.conv_cl(a, m[idx].weight, m[idx].bias, pad=1, bias_slot=sl); tap(idx, y)
+                a = Fn.instnorm_cl(y, relu=True, bias_slot=sl); tap(idx + 1, a); tap(idx + 2, a)
                 a = Fn.blur_down_cl(a); tap(idx + 3, a)
                 idx += 4
             if nb > 0:
@@ -237,9 +244,10 @@ class ResnetGenerator(nn.Module):
                 a = P
             for i in range(nd):
                 a = Fn.blur_up_cl(a); tap(idx, a)
-                y = Fn.conv_cl(a, m[idx + 1].weight, m[idx + 1].bias, pad=1); tap(idx + 1, y)
+                sl = slot(idx + 1)
+                y = Fn.conv_cl(a, m[idx + 1].weight, m[idx + 1].bias, pad=1, bias_slot=sl); tap(idx + 1, y)
                 op = 3 if i + 1 == nd else 0
-                a = Fn.instnorm_cl(y, relu=True, out_pad=op); tap(idx + 2, interior(a, op)); tap(idx + 3, interior(a, op))
+                a = Fn.instnorm_cl(y, relu=True, out_pad=op, bias_slot=sl); tap(idx + 2, interior(a, op)); tap(idx + 3, interior(a, op))
                 idx += 4
             tap(idx, a)                                     # ReflectionPad2d(3) output
             if (idx + 1) in want:

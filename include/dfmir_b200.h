@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DFMIR_ABI_VERSION 3
+#define DFMIR_ABI_VERSION 4
 
 #define DFMIR_INTERP_LINEAR 0
 #define DFMIR_INTERP_NEAREST 1
@@ -163,6 +163,12 @@ int dfmir_instnorm_fwd(const float* x, const float* res, float* y, float* stats,
 int dfmir_instnorm_bwd(const float* dy, const float* x, const float* stats, float* dx, float* dres, void* ws,
                        size_t ws_bytes, int N, int H, int W, int C, int relu, int out_pad, int res_pad,
                        void* stream);
+/* Same, plus dbias (C) = sum of dx over samples and pixels: dx is the output gradient of the convolution that
+ * produced x (nn.Conv2d(..., bias=True) followed by InstanceNorm2d, models/networks.py:983-984, 1201-1202), so this is
+ * that convolution's bias gradient without another pass over dx.  dbias NULL: identical to dfmir_instnorm_bwd. */
+int dfmir_instnorm_bwd_bias(const float* dy, const float* x, const float* stats, float* dx, float* dres, float* dbias,
+                            void* ws, size_t ws_bytes, int N, int H, int W, int C, int relu, int out_pad, int res_pad,
+                            void* stream);
 /* ---- nn.ReflectionPad2d — models/networks.py:982,1022 */
 int dfmir_pad_reflect_fwd(const float* x, float* y, int N, int H, int W, int C, int pad, void* stream);
 int dfmir_pad_reflect_bwd(const float* dy, float* dx, int N, int H, int W, int C, int pad, void* stream);
