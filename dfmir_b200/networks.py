@@ -210,7 +210,10 @@ class ResnetGenerator(nn.Module):
         def tap(idx, x_cl):
             """record the output of reference layer `idx` (channels-last tensor or view)"""
             if idx in want:
-                feats[idx] = self._nchw(x_cl)
+                v = self._nchw(x_cl)
+                if x_cl._base is None and x_cl.is_contiguous():
+                    v._dfmir_cl = x_cl          # lets PatchSampleF's gather return a sparse gradient (functional.gather_patches)
+                feats[idx] = v
             if encode_only and idx == last:
                 raise _Stop()
 
