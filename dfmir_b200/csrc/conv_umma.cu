@@ -52,6 +52,7 @@ struct UmmaP {
   int flip;               // 1: use tap (taps-1-t) of the weight tensor (data gradient)
   int act;
   int per_sample;         // 1: the "tap" coordinate of the weight map is the sample index (batched A[b] * B[b]^T)
+  int accum;              // 1: y += result (CTA-pair kernel only: the residual branch's gradient is already in y)
   long long ys[5];        // output element strides n, d, h, w, c
 };
 
@@ -677,12 +678,22 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           if (vec_ok && n0 + c0 + 32 <= p.Cout) {
             float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
+            if (p.accum) {
+              float4 o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = dst[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[4 * i] += o[i].x; v[4 * i + 1] += o[i].y; v[4 * i + 2] += o[i].z; v[4 * i + 3] += o[i].w; }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (n0 + c0 + i < p.Cout) yp[(long long)(n0 + c0 + i) * p.ys[4]] = v[i];
+              if (n0 + c0 + i < p.Cout) {
+                float* q = yp + (long long)(n0 + c0 + i) * p.ys[4];
+                *q = p.accum ? *q + v[i] : v[i];
+              }
           }
         }
       }
@@ -745,7 +756,7 @@ int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
   }
   p.KD = K[0]; p.KH = K[1]; p.KW = K[2]; p.pad_d = P[0]; p.pad_h = P[1]; p.pad_w = P[2];
   p.D = O[0]; p.H = O[1]; p.W = O[2];
-  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act; p.per_sample = 0;
+  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act; p.per_sample = 0; p.accum = 0;
   const Strides5 os = spread(dgrad ? d->x_strides : d->y_strides, nd);
   p.ys[0] = os.n; p.ys[1] = os.d; p.ys[2] = os.h; p.ys[3] = os.w; p.ys[4] = os.c;
   // tile box TD x TH x TW = 128 voxels (powers of two, TW >= 8): the shape that wastes the fewest voxels on
@@ -890,6 +901,10 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   const bool narrow256 = p.Cout == 256 && ID == 1 && p.KD * p.KH * p.KW > 1 && eff16 < 0.72 && eff8 > eff16 * 1.08;
   if (narrow256) BN = 256;
   static const int pair = getenv("DFMIR_UMMA_PAIR") ? atoi(getenv("DFMIR_UMMA_PAIR")) : 1;
+  if (p.accum && !(pair && ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.Cin % KCH == 0 && p.ys[4] == 1 && p.Cout % 256 == 0)) {
+    dfmir_set_error("%s: accumulation into the output is implemented by the CTA-pair kernel (2-D 3x3, 256-channel tiles)", who);
+    return DFMIR_ERR_UNSUPPORTED;
+  }
   if (pair && ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.Cin % KCH == 0 && !p.per_sample && p.ys[4] == 1) {
     if (p.Cout % 256 == 0) return launch_pair<256>(act, as, IH, IW, w, bias, y, p, st, who);
     // DFMIR_UMMA_PAIR=2 also pairs the 128-channel layers: measured slower than the single-CTA 2 x 128 tiles (5.7 vs 5.2 ms / step)
@@ -976,6 +991,26 @@ extern "C" int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx,
                   dx, p, (cudaStream_t)stream, "dfmir_conv_umma_dgrad");
 }
 
+// Same product ADDED to dx (dx += conv(dy, flipped taps)): the ResnetBlock input receives the residual branch's
+// gradient first (dfmir_instnorm_bwd writes it, models/networks.py:1218-1221 out = x + conv_block(x)) and the
+// convolution branch's data gradient lands on top of it, instead of a separate add over both tensors.
+// DFMIR_ERR_UNSUPPORTED (nothing launched) unless the CTA-pair kernel covers the shape; dfmir_conv_umma_dgrad_acc_supported tells.
+extern "C" int dfmir_conv_umma_dgrad_acc_supported(const dfmir_conv_desc* d) {
+  static const int pair = getenv("DFMIR_UMMA_PAIR") ? atoi(getenv("DFMIR_UMMA_PAIR")) : 1;
+  if (!pair || !umma_shape_ok(d, 1) || d->nd != 2 || d->kernel[0] != 3 || d->kernel[1] != 3) return 0;
+  return d->Cin % 256 == 0 && d->Cout % KCH == 0 && d->x_strides[3] == 1;
+}
+
+extern "C" int dfmir_conv_umma_dgrad_acc(const float* dy, const float* w, float* dx, const dfmir_conv_desc* d, void* stream) {
+  UmmaP p;
+  int rc = fill_umma(p, d, 1, "dfmir_conv_umma_dgrad_acc");
+  if (rc) return rc;
+  DFMIR_CHECK_ARG(dy && w && dx, "dfmir_conv_umma_dgrad_acc: null pointer");
+  p.accum = 1;
+  return run_umma(dy, spread(d->y_strides, 2), 1, d->out_shape[0], d->out_shape[1], w, nullptr, dx, p, (cudaStream_t)stream,
+                  "dfmir_conv_umma_dgrad_acc");
+}
+
 // Batched C[b] (M x N) = A[b] (M x K) * B[b]^T (N x K), all row-major and dense, on the same tcgen05 kernel:
 // the M rows of a sample are the "pixels", K the input channels, and the weight map's tap coordinate selects
 // the sample.  Used for the PatchNCE logits S = Q K^T (models/patchnce.py:20,42) and their backward product.
@@ -989,7 +1024,7 @@ extern "C" int dfmir_bmm_nt_umma(const float* A, const float* B, float* C, int b
   p.N = batch; p.D = 1; p.H = 1; p.W = M; p.Cin = K; p.Cout = N;
   p.KD = p.KH = p.KW = 1; p.pad_d = p.pad_h = p.pad_w = 0;
   p.TD = 1; p.TH = 1; p.TW = 128; p.tiles_d = 1; p.tiles_h = 1; p.tiles_w = M / 128;
-  p.ptiles = batch * p.tiles_w; p.flip = 0; p.act = DFMIR_ACT_NONE; p.per_sample = 1;
+  p.ptiles = batch * p.tiles_w; p.flip = 0; p.act = DFMIR_ACT_NONE; p.per_sample = 1; p.accum = 0;
   p.ys[0] = (long long)M * N; p.ys[1] = 0; p.ys[2] = 0; p.ys[3] = N; p.ys[4] = 1;
   const int mt = N <= 64 ? 4 : 2;      // sub-tiles per work item of the tile configuration run_umma picks
   DFMIR_CHECK_ARG(p.tiles_w % mt == 0, "%s: M = %d must be a multiple of %d so that a work item stays inside one sample", who, M, 128 * mt);

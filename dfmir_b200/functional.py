@@ -121,8 +121,9 @@ class _ConvFn(torch.autograd.Function):
     """y = act(conv(x, w) + b); x (N,*S,Cin) channels-last (any strides), w (taps,Cin,Cout)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, kernel, stride, pad, act, planar_out, bias_slot=None):
+    def forward(ctx, x, w, bias, kernel, stride, pad, act, planar_out, bias_slot=None, res_slot=None):
         ctx.bias_slot = bias_slot if act == ACT_NONE else None
+        ctx.res_slot = res_slot
         _lib.require_cuda(x, w)
         x, w = _f32(x), _f32(w).contiguous()
         nd = len(kernel)
@@ -172,15 +173,28 @@ class _ConvFn(torch.autograd.Function):
         if tc and planar_out and Cout % 4 and stride == 1 and Cin % 4 == 0 and x.data_ptr() % 16 == 0:
             # planar flow head (2 or 3 output channels): its gradient as a channels-last copy padded to 4 channels,
             # so that both backward products run on the tensor-core kernels (TMA rows must be 16-byte multiples)
-            return _ConvFn._backward_padded_head(ctx, x, w, dy) + (None,)
+            return _ConvFn._backward_padded_head(ctx, x, w, dy) + (None, None)
+        pending = None
+        if ctx.res_slot is not None and ctx.res_slot.dres is not None:
+            pending, ctx.res_slot.dres = ctx.res_slot.dres, None         # gradient of the skip connection, shaped like x
         if ctx.needs_input_grad[0]:
-            dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
+            acc = (pending is not None and tc and tuple(pending.shape) == (N, *S, Cin) and pending.is_contiguous()
+                   and dy.data_ptr() % 16 == 0)
+            dx = pending if acc else torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
-            if tc and dy.data_ptr() % 16 == 0 and umma.supported(d, True):
-                umma.conv_dgrad(dy, w, dx, d, flops)
+            if acc and _lib.lib().dfmir_conv_umma_dgrad_acc_supported(ctypes.byref(d)):
+                _run(lambda: _lib.call("dfmir_conv_umma_dgrad_acc", dy, w, dx, ctypes.byref(d)), flops, "umma_dgrad")
+                pending = None
             else:
-                wt = w.transpose(1, 2).contiguous()
-                _run(lambda: _lib.call("dfmir_conv_dgrad", dy, wt, dx, ctypes.byref(d)), flops)
+                if acc:
+                    dx = torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
+                if tc and dy.data_ptr() % 16 == 0 and umma.supported(d, True):
+                    umma.conv_dgrad(dy, w, dx, d, flops)
+                else:
+                    wt = w.transpose(1, 2).contiguous()
+                    _run(lambda: _lib.call("dfmir_conv_dgrad", dy, wt, dx, ctypes.byref(d)), flops)
+            if pending is not None:
+                dx = dx + pending
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             dw = torch.zeros_like(w)
             db = torch.zeros(Cout, dtype=w.dtype, device=w.device) if has_bias else None
@@ -194,7 +208,7 @@ class _ConvFn(torch.autograd.Function):
                 _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops)
             if db_given is not None:
                 db = db_given if has_bias else None
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 def _backward_padded_head(ctx, x, w, dy):
@@ -279,7 +293,19 @@ class BiasGradSlot:
         self.db = None
 
 
-def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False, bias_slot=None):
+class ResidualGradSlot:
+    """Hand-over of the residual branch's gradient inside a ResnetBlock (out = x + conv_block(x)): the last
+    InstanceNorm's backward writes d(out)/d(x) of the skip connection into a buffer shaped like the block input and
+    parks it here instead of returning it; the first convolution's data gradient is then ADDED to that buffer by the
+    kernel's epilogue (dfmir_conv_umma_dgrad_acc) or, on the other engines, by one add.  Pass the same slot to the
+    block's first conv_cl(..., res_slot=) and to instnorm_cl(..., res=x, res_slot=)."""
+    __slots__ = ("dres",)
+
+    def __init__(self):
+        self.dres = None
+
+
+def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False, bias_slot=None, res_slot=None):
     """Convolution on a channels-last activation with a PyTorch-layout weight (Cout, Cin, *k).
     Returns (N,*O,Cout), or the planar (N,Cout,*O) when planar_out."""
     nd = weight.dim() - 2
@@ -287,13 +313,14 @@ def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False, bi
     pads = [pad] * nd if isinstance(pad, int) else list(pad)
     Cin = weight.shape[1]
     w = packed_weight(weight, x.shape[-1] - Cin)
-    return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out, bias_slot)
+    return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out, bias_slot, res_slot)
 
 
 class _InstNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, relu, out_pad, res_pad, eps, bias_slot=None):
+    def forward(ctx, x, res, relu, out_pad, res_pad, eps, bias_slot=None, res_slot=None):
         ctx.bias_slot = bias_slot
+        ctx.res_slot = res_slot if res is not None else None
         _lib.require_cuda(x)
         x = _f32(x).contiguous()
         N, H, W, C = x.shape
@@ -329,12 +356,14 @@ class _InstNormFn(torch.autograd.Function):
                   out_pad, res_pad)
         if slot is not None:
             slot.db = dbias
-        return dx, dres, None, None, None, None, None
+        if ctx.res_slot is not None and dres is not None:
+            ctx.res_slot.dres, dres = dres, None        # taken up by the block's first convolution backward
+        return dx, dres, None, None, None, None, None, None
 
 
-def instnorm_cl(x, relu=False, out_pad=0, res=None, res_pad=0, eps=1e-5, bias_slot=None):
+def instnorm_cl(x, relu=False, out_pad=0, res=None, res_pad=0, eps=1e-5, bias_slot=None, res_slot=None):
     """InstanceNorm2d(affine=False) [+ReLU] [+res] written with a reflected halo of width out_pad."""
-    return _InstNormFn.apply(x, res, relu, out_pad, res_pad, eps, bias_slot)
+    return _InstNormFn.apply(x, res, relu, out_pad, res_pad, eps, bias_slot, res_slot)
 
 
 class _PadReflectFn(torch.autograd.Function):
@@ -580,6 +609,8 @@ def gather_patches(feat, ids):
 
 
 SPARSE_TAP_GRAD = os.environ.get("DFMIR_SPARSE_TAP_GRAD", "1") != "0"
+if SPARSE_TAP_GRAD:
+    torch.sparse.check_sparse_tensor_invariants.disable()     # explicit opt-out: indices come from our own randperm slices
 
 
 def _split3(x, b_style):

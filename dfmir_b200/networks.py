@@ -143,10 +143,11 @@ class ResnetBlock(nn.Module):
         written with a halo of out_pad."""
         c1, c2 = self.conv_block[1], self.conv_block[5]
         s1, s2 = Fn.BiasGradSlot(), Fn.BiasGradSlot()      # conv bias gradients summed by the IN backward passes
-        y = Fn.conv_cl(P, c1.weight, c1.bias, bias_slot=s1)
+        rs = Fn.ResidualGradSlot()                         # skip-connection gradient, completed by c1's data gradient
+        y = Fn.conv_cl(P, c1.weight, c1.bias, bias_slot=s1, res_slot=rs)
         P1 = Fn.instnorm_cl(y, relu=True, out_pad=1, bias_slot=s1)
         y = Fn.conv_cl(P1, c2.weight, c2.bias, bias_slot=s2)
-        return Fn.instnorm_cl(y, relu=False, out_pad=out_pad, res=P, res_pad=1, bias_slot=s2)
+        return Fn.instnorm_cl(y, relu=False, out_pad=out_pad, res=P, res_pad=1, bias_slot=s2, res_slot=rs)
 
     def forward(self, x):
         P = Fn.pad_reflect_cl(x.permute(0, 2, 3, 1), 1)

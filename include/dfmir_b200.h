@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DFMIR_ABI_VERSION 4
+#define DFMIR_ABI_VERSION 5
 
 #define DFMIR_INTERP_LINEAR 0
 #define DFMIR_INTERP_NEAREST 1
@@ -140,8 +140,12 @@ int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad);
 int dfmir_conv_umma_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
                         void* stream);
 int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx, const dfmir_conv_desc* d, void* stream);
-/* tcgen05 weight gradient (2-D, stride 1, channels-last x and dy; one of Cin/Cout a multiple of 128, the other
- * in {64,128,256k}): split-K over output pixels, TF32 operands, fp32 accumulate in TMEM, red.add into
+/* dx += data gradient (the ResnetBlock input already holds the residual branch's gradient, models/networks.py:1218-1221):
+ * covered by the CTA-pair kernel (2-D 3x3, Cin a multiple of 256); _supported tells, else DFMIR_ERR_UNSUPPORTED. */
+int dfmir_conv_umma_dgrad_acc_supported(const dfmir_conv_desc* d);
+int dfmir_conv_umma_dgrad_acc(const float* dy, const float* w, float* dx, const dfmir_conv_desc* d, void* stream);
+/* tcgen05 weight gradient (2-D / 3-D, stride 1, channels-last x and dy, channel counts multiples of 4; >= 16 unless
+ * the kernel is 3x3 / 3x3x3): split-K over output voxels, TF32 operands, fp32 accumulate in TMEM, red.add into
  * dw [tap][Cin][Cout] / db [Cout] (nullable) — both ACCUMULATED into: zero-fill them first. */
 int dfmir_conv_umma_wgrad_supported(const dfmir_conv_desc* d);
 int dfmir_conv_umma_wgrad(const float* x, const float* dy, float* dw, float* db, const dfmir_conv_desc* d,

@@ -129,7 +129,7 @@ def test_vxm_default_features_step_full_size(monkeypatch):
             grad = losses.Grad_Loss(dim=3)(flow)
         (ncc + 0.02 * grad).backward()
         g = torch.cat([p.grad.flatten() for p in R.parameters() if p.grad is not None])
-        return y.detach(), flow.detach(), float(ncc), float(grad), g
+        return y.detach(), flow.detach(), float(ncc.detach()), float(grad.detach()), g
 
     default = Fn.CONV_ENGINE
     y1, f1, n1, g1, gr1 = step(default, True)
