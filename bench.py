@@ -7,7 +7,11 @@ Workload (BASELINE.json configs[1]): 2-D 256x256, batch 16 MR->CT pairs per GPU,
 REGISTRATIONModel.optimize_parameters (ResnetGenerator-9blocks x (2 full + 6 encoder passes),
 VoxelMorph-2D + VecInt, PatchNCE x3, masked L1 x2, smoothing, backward, 3 Adam steps), synthetic
 images, random-initialised weights.  One process per GPU (torchrun for N > 1, NCCL gradient
-all-reduce); weak scaling (per-GPU batch fixed).  Prints ONE JSON line on rank 0.
+all-reduce); weak scaling (per-GPU batch fixed).  After the warm-up the step is captured into one CUDA graph
+(REGISTRATIONModel.capture_step; DFMIR_CUDA_GRAPH=0 keeps eager launches) and K replays are timed with the inputs
+resident (`value`) and through set_input + get_current_losses (`e2e`); K further eager steps with CUDA events
+around every convolution launch give the `roofline` / `kernels` figures.  Prints ONE JSON line on rank 0.
+`--workload 3d`: VoxelMorph-3D step (configs[2]; `--shape3d 160,192,160 --features3d default` for configs[3]).
 
 `--impl reference` times the reference's CPU PyTorch path (oracle/torch_port.py, pinned to the
 reference's own step by tests/test_oracle_nets.py) on the host cores, one pair per step.

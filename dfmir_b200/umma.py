@@ -1,6 +1,7 @@
-"""tcgen05 (UMMA) convolution engine bindings: which layer shapes run on the tensor cores
-(csrc/conv_umma.cu) and the calls into libdfmir_b200.so for them.  Everything else, and the weight
-gradient for now, runs on the fp32 CUDA-core path (csrc/conv_simt.cu)."""
+"""tcgen05 (UMMA) convolution engine bindings: which layer shapes run on the tensor cores (csrc/conv_umma.cu:
+forward / data gradient; csrc/conv_umma_wgrad.cu: weight gradient) and the calls into libdfmir_b200.so for them.
+Everything else (strided, one-channel and tiny layers) runs on the fp32 CUDA-core path (csrc/conv_simt.cu,
+csrc/conv_thin.cu)."""
 import ctypes
 import weakref
 
