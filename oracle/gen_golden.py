@@ -283,6 +283,29 @@ def gen_nets():
     save("nets", **out)
 
 
+def gen_nets3d():
+    """VxmDense 3-D with the reference's DEFAULT U-Net features (vxm/networks.py:9-14; the network of BASELINE
+    configs[3]) on a 16 x 32 x 16 volume pair, not bidirectional: forward (registration=True) + backward."""
+    import_reference()
+    import models.voxelmorph.torchvoxelmorph as rvxm
+    out = {}
+    shape = (16, 32, 16)
+    torch.manual_seed(17)
+    R = rvxm.networks.VxmDense(shape, int_steps=7, bidir=False)
+    with torch.no_grad():   # a visible deformation: the reference initialises the flow head at 1e-5
+        R.flow.weight.mul_(2e4)
+    src = t(gi.image_textured(241, 1, shape)).requires_grad_()
+    tgt = t(gi.image_textured(242, 1, shape))
+    ys, flow = R(src, tgt, registration=True)
+    out["R3d/y_source"] = ys.detach().numpy(); out["R3d/pos_flow"] = flow.detach().numpy()
+    loss = (ys * t(gi.weights(243, tuple(ys.shape), 1.0))).sum() + (flow * t(gi.weights(245, tuple(flow.shape), 0.1))).sum()
+    loss.backward()
+    out["R3d/d_src"] = src.grad.numpy()
+    out.update(sd_np(R.state_dict(), "R3d/sd"))
+    out.update({f"R3d/grad/{k}": v.grad.numpy() for k, v in R.named_parameters()})
+    save("nets3d", **out)
+
+
 def gen_step():
     """One full REGISTRATIONModel.optimize_parameters on CPU (reference code, B = 2, 64x64, ngf 8)."""
     import_reference()
@@ -336,7 +359,7 @@ def gen_step():
     shutil.rmtree(work, ignore_errors=True)
 
 
-SECTIONS = {"ops": gen_ops, "nets": gen_nets, "step": gen_step}
+SECTIONS = {"ops": gen_ops, "nets": gen_nets, "nets3d": gen_nets3d, "step": gen_step}
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())

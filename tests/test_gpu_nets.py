@@ -256,6 +256,31 @@ def test_patch_sample_and_nce_vs_reference(golden, orc, monkeypatch):
         close(p.grad, want, 1e-3 * max(1e-6, np.abs(want).max()), k)
 
 
+def test_vxm_dense_3d_default_features_vs_reference(golden):
+    """VxmDense with the reference's default features (the BASELINE configs[3] network) on 16 x 32 x 16, pinned to the
+    reference's own forward / backward (oracle/gen_golden.py: nets3d)."""
+    from dfmir_b200 import vxm
+    g = golden("nets3d")
+    shape = (16, 32, 16)
+    R = vxm.VxmDense(shape, int_steps=7, bidir=False)
+    missing = R.load_state_dict(sd_of(g, "R3d/sd"), strict=False)
+    assert all(k.endswith(".grid") for k in missing.missing_keys) and not missing.unexpected_keys
+    R.cuda()
+    src = cu(gi.image_textured(241, 1, shape)).requires_grad_()
+    tgt = cu(gi.image_textured(242, 1, shape))
+    ys, flow = R(src, tgt, registration=True)
+    close(flow, g["R3d/pos_flow"], 2e-5, "pos_flow")
+    close(ys, g["R3d/y_source"], 2e-5)
+    ys_f, flow_f, _, _ = R.forward_with_losses(src, tgt, win=9)          # the fused launch gives the same field / volume
+    assert torch.equal(flow_f, flow) and torch.equal(ys_f, ys)
+    loss = (ys * cu(gi.weights(243, tuple(ys.shape), 1.0))).sum() + (flow * cu(gi.weights(245, tuple(flow.shape), 0.1))).sum()
+    loss.backward()
+    close(src.grad, g["R3d/d_src"], 1e-4 * np.abs(g["R3d/d_src"]).max())
+    for k, p in R.named_parameters():
+        want = g[f"R3d/grad/{k}"]
+        close(p.grad, want, 1e-3 * max(1e-6, np.abs(want).max()), k)
+
+
 @pytest.mark.parametrize("name,shape,feats", [("R2", (64, 64), [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]]),
                                               ("R3", (16, 16, 16), [[8, 16, 16], [16, 16, 16, 8, 8]])])
 def test_vxm_dense_vs_reference(name, shape, feats, golden):

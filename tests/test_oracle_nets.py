@@ -55,6 +55,17 @@ def test_vxm_dense(name, shape, n_enc, n_dec, golden, nets):
     np.testing.assert_allclose(yt, g[name + "/y_target"], atol=2e-5)
 
 
+def test_vxm_dense_3d_default_features(golden, nets):
+    """The network of BASELINE configs[3]: the reference's default U-Net features (4 encoder / 7 decoder convs)."""
+    g = golden("nets3d")
+    sd = sd_of(g, "R3d/sd")
+    shape = (16, 32, 16)
+    src, tgt = gi.image_textured(241, 1, shape), gi.image_textured(242, 1, shape)
+    ys, _, flow = nets.vxm_dense(src, tgt, sd, 4, 7)
+    np.testing.assert_allclose(flow, g["R3d/pos_flow"], atol=2e-5)
+    np.testing.assert_allclose(ys, g["R3d/y_source"], atol=2e-5)
+
+
 def test_patch_sample_and_nce(golden, orc, nets):
     g = golden("nets")
     sd = sd_of(g, "F/sd")
