@@ -3,6 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
 
+The ONE JSON line carries the headline workload (BASELINE configs[1], below) at top level and, under `workloads`, the
+3-D registration workloads of configs[2] (128^3, batch 2 / GPU, 6-level U-Net) and configs[3]'s shape (160x192x160,
+batch 1 / GPU, the reference's default features), each with its own value / e2e / kernel roofline and (N = 1) CPU leg,
+so that the driver's 1/2/4/8-GPU runs record them too.  At N = 1 it also carries `parity` (the step's six losses, NCC
+and warp indices against the oracle on the same inputs, computed outside the timed regions) and
+`gpu_library_baseline` (the reference's PyTorch path - cuDNN TF32 + ATen - on the same B200, informational).
+
 Workload (BASELINE.json configs[1]): 2-D 256x256, batch 16 MR->CT pairs per GPU, one full
 REGISTRATIONModel.optimize_parameters (ResnetGenerator-9blocks x (2 full + 6 encoder passes),
 VoxelMorph-2D + VecInt, PatchNCE x3, masked L1 x2, smoothing, backward, 3 Adam steps), synthetic
@@ -103,37 +110,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args):
-    """The reference's CPU PyTorch path (oracle/torch_port.Step) on all host cores: one pair per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import torch_port as tp
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    S = args.size
-    G, Fd, R = tp.random_state_dicts(crop=S)
-    A, B = synthetic_pair(1, S, 1234)
-    st = tp.Step(G, Fd, R, n_blocks=9, batch_size=1, dvf_image=torch.zeros(1, 3, S, S))
-    for _ in range(args.warmup):
-        st.step(A, B)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        st.step(A, B)
-    dt = time.perf_counter() - t0
-    v = args.steps / dt
-    sample = f"{args.steps} steps of 1 pair (batch 1) at {S}x{S}, torch CPU fp32, {cores} threads"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"2D {S}x{S} translation+registration fwd/bwd+Adam (BASELINE configs[1]); CPU sample: batch 1 per step",
-                   "batch_per_step": 1},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+def synthetic_volumes(B, shape, seed):
+    g = torch.Generator().manual_seed(seed)
+
+    def vol():
+        x = torch.randn(B, 1, *shape, generator=g)
+        k = torch.ones(1, 1, 5, 5, 5) / 125.0
+        for _ in range(2):
+            x = torch.nn.functional.conv3d(x, k, padding=2)
+        return torch.tanh(3 * x / x.std()).contiguous()
+    return vol(), vol()
 
 
-def cpu_baseline(S, budget_s=25.0):
+FEATS_6LEVEL = [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]]
+FEATS_DEFAULT = [[16, 32, 32, 32], [32, 32, 32, 32, 32, 16, 16]]      # vxm/networks.py:9-14
+WORKLOADS_3D = {          # name -> (shape, batch per GPU, features, BASELINE config index)
+    "3d_128": ((128, 128, 128), 2, "6level", 2),
+    "3d_160x192x160": ((160, 192, 160), 1, "default", 3),
+}
+
+
+def conv_flops_3d(shape, six_level):
+    """VxmDense-3D 128^3 6-level 284.6 GFLOP per pair (95.0 fwd + 189.6 bwd); default features at
+    160x192x160 1708.1; both scale with the voxel count."""
+    vox = shape[0] * shape[1] * shape[2]
+    return 284.6e9 * vox / 128 ** 3 if six_level else 1708.1e9 * vox / (160 * 192 * 160)
+
+
+def cpu_baseline_2d(S, budget_s=20.0):
     from oracle import torch_port as tp
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -147,20 +151,146 @@ def cpu_baseline(S, budget_s=25.0):
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} steps of 1 pair (batch 1) at {S}x{S} after 1 warm-up, oracle/torch_port.py (torch CPU fp32, {cores} threads)"}
+            "sample": f"{n} steps of 1 pair (batch 1) at {S}x{S} after 1 warm-up, oracle/torch_port.Step (torch CPU fp32, {cores} threads)"}
 
 
-def run_ours(args):
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+def cpu_baseline_3d(shape, features, max_steps=1):
+    """The reference's composition for the 3-D workloads (VxmDense-3D + NCC_Loss[9^3] + Grad_Loss, fwd + bwd + Adam) on
+    the host cores: oracle/torch_port.Step3D, one pair per step, no warm-up (a step takes 10 - 40 s)."""
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    feats = FEATS_6LEVEL if features == "6level" else FEATS_DEFAULT
+    st = tp.Step3D(tp.random_state_dict_r3d(feats), feats)
+    A, B = synthetic_volumes(1, shape, 77)
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_steps:
+        st.step(A, B)
+        n += 1
+    dt = time.perf_counter() - t0
+    name = "x".join(str(v) for v in shape)
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} step(s) of 1 pair (batch 1) at {name}, no warm-up, oracle/torch_port.Step3D (torch CPU fp32, {cores} threads)"}
+
+
+def run_reference(args):
+    """The reference's CPU PyTorch path (oracle/torch_port: Step for the 2-D headline, Step3D for the 3-D workloads) on all
+    host cores, one pair per step."""
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank != 0:
+        return
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S = args.size
+    G, Fd, R = tp.random_state_dicts(crop=S)
+    A, B = synthetic_pair(1, S, 1234)
+    st = tp.Step(G, Fd, R, n_blocks=9, batch_size=1, dvf_image=torch.zeros(1, 3, S, S))
+    for _ in range(min(args.warmup, 2)):
+        st.step(A, B)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st.step(A, B)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} steps of 1 pair (batch 1) at {S}x{S}, torch CPU fp32, {cores} threads"
+    workloads = {}
+    if not args.no_3d:
+        for name, (shape, _, feats, cfg) in WORKLOADS_3D.items():
+            cb = cpu_baseline_3d(shape, feats)
+            workloads[name] = {"value": cb["value"], "unit": UNIT, "cpu_baseline": cb,
+                               "config": {"workload": f"3D {name[3:]} VoxelMorph-3D + NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[{cfg}]); CPU sample: batch 1"}}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"2D {S}x{S} translation+registration fwd/bwd+Adam (BASELINE configs[1]); CPU sample: batch 1 per step",
+                   "batch_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "workloads": workloads}))
+
+
+class Ctx:
+    """Process-group plumbing shared by the legs of one bench run."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K calls bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks (ms)."""
+        self.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        self.barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def committed_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from this round's `ncu --set full`
+    capture (profiles/<name>; regenerated by tools/ncu_summary.py whenever the kernel changes)."""
+    for fn in (name, name.replace("r2_", "r1_")):
+        tpath = os.path.join(ROOT, "profiles", fn)
+        if os.path.exists(tpath):
+            d = json.load(open(tpath))
+            return d.get("traffic_bytes_per_launch"), f"profiles/{fn}: {d.get('kernel', '')} {d.get('note', '')}".strip()
+    return None, None
+
+
+def roofline_block(kinds, steps, step_ms, pk, pk_src, kernel_name, traffic_file):
+    """Tensor-pipe roofline of the dominant kernel group (tcgen05 implicit-GEMM forward + data gradient): algorithmic
+    FLOPs (2*M*N*K per launch) over the CUDA-event duration of those launches, against the measured bf16 peak."""
+    dom = [kinds.get(k, (0.0, 0.0, 0, 0.0)) for k in ("umma_fwd", "umma_dgrad")]
+    dom_ms, dom_fl, dom_n, dom_by = (sum(v[i] for v in dom) for i in range(4))
+    achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
+    peak = pk["bf16_tflops_sustained"]
+    traffic, tnote = committed_traffic(traffic_file)
+    return {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": f"bf16_tflops_sustained, {pk_src}; kind::tf32 issues at half the bf16 rate, so the TF32 ceiling of "
+                           "this kernel is peak/2",
+            "frac_of_tf32_ceiling": achieved / (peak / 2.0),
+            "flops_per_launch": dom_fl / dom_n if dom_n else 0.0, "launch_ms": dom_ms / dom_n if dom_n else 0.0,
+            "launches_per_step": dom_n / steps, "share_of_step": dom_ms / step_ms if step_ms > 0 else None,
+            "hbm_view": {"algorithmic_bytes_per_launch": dom_by / dom_n if dom_n else 0.0,
+                         "achieved_gbs": dom_by / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0, "peak_gbs": pk["hbm_gbs"],
+                         "frac": (dom_by / (dom_ms / 1e3) / 1e9 / pk["hbm_gbs"]) if dom_ms > 0 else 0.0,
+                         "note": "operand + result bytes (activations in, activations out, weights) of the same launches"},
+            "measured": f"CUDA events around every launch of these kernels over {steps} further steps of the same workload",
+            "traffic": traffic, "traffic_note": tnote}
+
+
+def per_kind(kinds, steps):
+    return {k: {"ms_per_step": v[0] / steps, "tflops": (v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0),
+                "launches_per_step": v[2] / steps} for k, v in sorted(kinds.items())}
+
+
+def bench_2d(args, ctx):
     from dfmir_b200 import _lib, registration_model as rm
     from dfmir_b200 import functional as Fn
-
+    world, rank, local = ctx.world, ctx.rank, ctx.local
     B, S = args.batch, args.size
     use_graph = os.environ.get("DFMIR_CUDA_GRAPH", "1") != "0"
     opt = rm.default_options(batch_size=B, crop_size=S, load_size=S, gpu_ids=[local], cuda_graph=use_graph)
@@ -172,25 +302,6 @@ def run_ours(args):
         model.data_dependent_initialize(data)
         model.setup(opt)
         model.parallelize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(steps):
-            fn()
-        e.record()
-        barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
     model.set_input(data)
 
     def step_resident():
@@ -201,14 +312,10 @@ def run_ours(args):
         model.optimize_parameters()
         model.get_current_losses()
 
-    for _ in range(args.warmup):
-        step_resident()
     # the first second after start-up runs ~8 % slower than steady state (allocator growth, clock ramp): keep warming,
-    # untimed, for a fixed number of further steps (~1 s) so that the K timed steps below measure the steady state
-    for _ in range(EXTRA_WARMUP_2D):            # a fixed count: every rank must run the same number of all-reduces
+    # untimed, for a fixed number of further steps so that the K timed steps below measure the steady state
+    for _ in range(args.warmup + EXTRA_WARMUP_2D):      # a fixed count: every rank must run the same number of all-reduces
         step_resident()
-    # the whole step (forward, losses, backward, gradient all-reduce, Adam) as one CUDA graph: same kernels, no
-    # per-launch host work (DFMIR_CUDA_GRAPH=0: eager launches)
     graphed, graph_note = False, None
     if use_graph:
         try:
@@ -223,38 +330,30 @@ def run_ours(args):
             step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.launch_count_reset()
-    ms = timed(step_resident, args.steps)
+    ms = ctx.timed(step_resident, args.steps)
     launches = model.graph_launches_per_step * args.steps if graphed else _lib.launch_count()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = ctx.timed(step_e2e, args.steps)
+    losses = model.get_current_losses()
     model._graph = None                          # the per-kernel event pass below needs eager launches
-    # per-kernel durations for the roofline: the same K steps once more with a CUDA-event pair around every convolution
-    # launch (kept out of the timed regions above: ~1000 event records per step cost host time the step no longer hides)
     prof = Fn.ConvProfile()
     Fn.PROFILE = prof
-    ms_prof = timed(step_resident, args.steps)
+    ms_prof = ctx.timed(step_resident, args.steps)
     Fn.PROFILE = None
     kinds = prof.by_kind()
     conv_ms, conv_flops, conv_calls = prof.total()
     clocks = sampler.stop() if sampler else None
-
+    del model
+    rm_cleanup()
     if rank != 0:
-        return
+        return None
     pk, pk_src = peaks()
     value = B * world * args.steps / (ms / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
-    # dominant kernel: the tcgen05 implicit-GEMM convolution (forward and data gradient are the same kernel)
-    dom_ms = sum(kinds.get(k, (0, 0, 0))[0] for k in ("umma_fwd", "umma_dgrad"))
-    dom_fl = sum(kinds.get(k, (0, 0, 0))[1] for k in ("umma_fwd", "umma_dgrad"))
-    dom_n = sum(kinds.get(k, (0, 0, 0))[2] for k in ("umma_fwd", "umma_dgrad"))
-    achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else 0.0
-    peak = pk["bf16_tflops_sustained"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
-    per_kind = {k: {"ms_per_step": v[0] / args.steps, "tflops": (v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0),
-                    "launches_per_step": v[2] / args.steps} for k, v in sorted(kinds.items())}
-    line = {
+    roof = roofline_block(kinds, args.steps, ms, pk, pk_src,
+                          "conv_umma_pair_kernel / conv_umma_halo_kernel / conv_umma_kernel (tcgen05 implicit-GEMM convolution, forward + data gradient)",
+                          "r2_dominant_kernel.json")
+    roof["measured"] += f" ({ms_prof / args.steps:.1f} ms/step with the event records)"
+    return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32" if prof.umma_calls else "f32", "data": "synthetic",
@@ -272,147 +371,240 @@ def run_ours(args):
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * B * S * S * 4), "d2h_bytes_per_step": 6 * 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv_umma_pair_kernel / conv_umma_halo_kernel / conv_umma_kernel (tcgen05 implicit-GEMM convolution, forward + data gradient)",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "peak_source": f"bf16_tflops_sustained, {pk_src}; kind::tf32 issues at half the bf16 rate, so the "
-                                    "TF32 ceiling of this kernel is peak/2",
-                     "frac_of_tf32_ceiling": achieved / (peak / 2.0),
-                     "flops_per_launch": dom_fl / dom_n if dom_n else 0.0, "launch_ms": dom_ms / dom_n if dom_n else 0.0,
-                     "launches_per_step": dom_n / args.steps, "share_of_step": dom_ms / ms if ms > 0 else None,
-                     "measured": f"CUDA events around every launch of these kernels over {args.steps} further steps of the same workload "
-                                 f"({ms_prof / args.steps:.1f} ms/step with the event records)",
-                     "traffic": traffic,
-                     "traffic_note": "dram bytes of one ResnetBlock-conv launch (batch 16) from profiles/r1_dominant_kernel.json"
-                                     if traffic else None},
-        "kernels": per_kind,
+        "losses_last_step": losses,
+        "roofline": roof,
+        "kernels": per_kind(kinds, args.steps),
         "conv_total": {"ms_per_step": conv_ms / args.steps, "tflops": conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0,
                        "flops_per_step": conv_flops / args.steps, "share_of_step": conv_ms / ms if ms > 0 else None},
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(S)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def rm_cleanup():
+    import gc
+    from dfmir_b200 import functional as Fn, umma, losses
+    Fn._pack_cache.clear(); umma._kmajor_cache.clear(); Fn._ws_cache.clear(); losses._ws_cache.clear()
+    gc.collect()
+    torch.cuda.empty_cache()
 
 
 EXTRA_WARMUP_2D = 12
-EXTRA_WARMUP_3D = 40
+EXTRA_WARMUP_3D = 30
 
 
-def run_ours_3d(args):
-    """BASELINE configs[2]: VoxelMorph-3D (6-level features) on 128^3 volume pairs, batch 2 per GPU: U-Net fwd,
-    fused integrate -> resize -> warp -> NCC + Grad (one cooperative launch), backward, Adam.  Weak scaling."""
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from dfmir_b200 import _lib, vxm
-    B = args.batch3d
-    shape = tuple(int(v) for v in args.shape3d.split(",")) if args.shape3d else (args.size3d,) * 3
+def bench_3d(args, ctx, shape, B, features, cfg_no, steps=None):
+    """VoxelMorph-3D registration step (dfmir_b200.vxm_trainer.VxmRegistrationTrainer): U-Net forward, ONE launch for
+    integrate -> resize -> warp -> NCC + Grad, backward, Adam; batch B per GPU, weak scaling."""
+    from dfmir_b200 import _lib
+    from dfmir_b200 import functional as Fn
+    from dfmir_b200.vxm_trainer import VxmRegistrationTrainer
+    world, rank, local = ctx.world, ctx.rank, ctx.local
+    steps = steps or args.steps
+    six_level = features == "6level"
     vox = shape[0] * shape[1] * shape[2]
-    six_level = args.features3d == "6level"
+    use_graph = os.environ.get("DFMIR_CUDA_GRAPH", "1") != "0"
     torch.manual_seed(1234)
-    feats = [[16, 32, 32, 64, 64, 64], [64, 64, 64, 32, 32, 32, 16]] if six_level else None   # None: vxm/networks.py:9-14 defaults
-    R = vxm.VxmDense(shape, feats, int_steps=7, bidir=False).cuda()
-    params = [p for p in R.parameters() if p.requires_grad]
-    flat = None
-    if world > 1:
-        for t in list(R.parameters()) + list(R.buffers()):
-            dist.broadcast(t.data, src=0)
-        flat = torch.zeros(sum(p.numel() for p in params), device="cuda")
-        off = 0
-        for p in params:
-            p.grad = flat[off:off + p.numel()].view_as(p); off += p.numel()
-    optim = torch.optim.Adam(params, lr=2e-4, betas=(0.5, 0.999))
-    g = torch.Generator().manual_seed(77 + rank)
-    def vol():
-        x = torch.randn(B, 1, *shape, generator=g)
-        k = torch.ones(1, 1, 5, 5, 5) / 125.0
-        for _ in range(2):
-            x = torch.nn.functional.conv3d(x, k, padding=2)
-        return torch.tanh(3 * x / x.std()).contiguous().pin_memory()
-    hA, hB = vol(), vol()
-    state = {"A": hA.cuda(), "B": hB.cuda(), "loss": None}
+    tr = VxmRegistrationTrainer(shape, FEATS_6LEVEL if six_level else None, int_steps=7, win=9, lambda_grad=0.02,
+                                device=torch.device("cuda", local), cuda_graph=use_graph)
+    tr.parallelize()
+    hA, hB = (t.pin_memory() for t in synthetic_volumes(B, shape, 77 + rank))
+    tr.set_input(hA, hB)
 
     def step_resident():
-        if flat is not None:
-            flat.zero_()
-        else:
-            optim.zero_grad(set_to_none=False) if params[0].grad is not None else None
-        y, flow, ncc, grad = R.forward_with_losses(state["A"], state["B"], win=9)
-        loss = ncc + 0.02 * grad
-        loss.backward()
-        if flat is not None:
-            dist.all_reduce(flat); flat.mul_(1.0 / world)
-        optim.step()
-        state["loss"] = loss.detach()
+        tr.optimize_parameters()
 
     def step_e2e():
-        state["A"] = hA.cuda(non_blocking=True); state["B"] = hB.cuda(non_blocking=True)
-        step_resident()
-        float(state["loss"])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(steps):
-            fn()
-        e.record()
-        barrier()
-        ms = torch.tensor([s.elapsed_time(e)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        tr.set_input(hA, hB)
+        tr.optimize_parameters()
+        tr.get_current_losses()
 
     for _ in range(args.warmup + EXTRA_WARMUP_3D):
         step_resident()
+    graphed, graph_note = False, None
+    if use_graph:
+        try:
+            tr.capture_step()
+            graphed = True
+        except Exception as exc:
+            tr._graph = None
+            graph_note = f"capture failed, eager launches: {type(exc).__name__}: {str(exc)[:200]}"
+            print("bench.py (3d): " + graph_note, file=sys.stderr)
+            torch.cuda.synchronize()
+        for _ in range(3):
+            step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.launch_count_reset()
-    ms = timed(step_resident, args.steps)
-    launches = _lib.launch_count()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms = ctx.timed(step_resident, steps)
+    launches = tr.graph_launches_per_step * steps if graphed else _lib.launch_count()
+    ms_e2e = ctx.timed(step_e2e, steps)
+    losses = tr.get_current_losses()
+    tr._graph = None
+    prof = Fn.ConvProfile()
+    Fn.PROFILE = prof
+    ctx.timed(step_resident, steps)
+    Fn.PROFILE = None
+    kinds = prof.by_kind()
+    conv_ms, conv_flops, _ = prof.total()
     clocks = sampler.stop() if sampler else None
+    del tr
+    rm_cleanup()
     if rank != 0:
-        return
-    # SURVEY 8d: VxmDense-3D 128^3 6-level 284.6 GFLOP per pair (95.0 fwd + 189.6 bwd); default features at
-    # 160x192x160 1708.1; both scale with the voxel count
-    flops = (284.6e9 * vox / 128 ** 3 if six_level else 1708.1e9 * vox / (160 * 192 * 160)) * B
+        return None
+    flops = conv_flops_3d(shape, six_level) * B
     name = "x".join(str(v) for v in shape)
-    cfg_no = 3 if shape == (160, 192, 160) else 2
     pk, pk_src = peaks()
-    line = {
-        "metric": METRIC, "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32", "data": "synthetic",
+    roof = roofline_block(kinds, steps, ms, pk, pk_src,
+                          "conv_umma_halo_kernel (tcgen05 implicit-GEMM 3x3x3 convolution, 5-D TMA halo boxes; forward + data gradient)",
+                          f"r2_dominant_kernel_{'3d_128' if six_level else '3d_160'}.json")
+    return {
+        "value": B * world * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "ms_per_step": ms / steps, "scaling": "weak", "dtype": "tf32",
         "config": {"workload": f"3D {name} batch={B}/GPU VoxelMorph-3D ({'6-level' if six_level else 'default'} features) + VecInt + "
                                f"NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[{cfg_no}])",
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "arithmetic": "fp32 storage; stride-1 convolutions with >= 16 channels on tcgen05 kind::tf32 (forward, data and weight "
-                                 "gradient, 5-D TMA boxes); the stride-2 encoder, the 2-channel first layer and the backward of the planar "
-                                 "flow head on fp32 CUDA cores; warp / VecInt / NCC / Grad fp32",
-                   "l2_policy": "inputs larger than L2: full-resolution activations are 34 channels x 8 MB per volume"},
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graphed,
+                   **({"cuda_graph_note": graph_note} if graph_note else {}),
+                   "l2_policy": "inputs larger than L2: full-resolution activations are 16-36 channels x 8-20 MB per volume"},
         "clocks": clocks,
-        "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(2 * B * vox * 4), "d2h_bytes_per_step": 4},
-        "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "all convolution kernels of the step (conv_umma_halo_kernel, conv_wgrad_umma_kernel, fp32 kernels for the strided / thin layers)",
-                     "achieved": flops * args.steps / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": flops * args.steps / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
-                     "peak_source": f"bf16_tflops_sustained, {pk_src}; whole-step algorithmic conv FLOPs over step time (not a single kernel)",
-                     "traffic": None},
+        "e2e": {"value": B * world * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(2 * B * vox * 4), "d2h_bytes_per_step": 8},
+        "gpu_launches": launches, "losses_last_step": losses,
+        "roofline": roof,
+        "kernels": per_kind(kinds, steps),
+        "conv_total": {"ms_per_step": conv_ms / steps, "share_of_step": conv_ms / ms if ms > 0 else None,
+                       "algorithmic_tflops_of_step": flops * steps / (ms / 1e3) / 1e12,
+                       "frac_of_bf16_peak": flops * steps / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"]},
     }
+
+
+def parity_block(S=256):
+    """The benchmarked network (ngf 64, 9 blocks, default engine) on ONE pair against the oracle, same weights / inputs /
+    patch ids, outside any timed region: max |d| of the six logged losses vs oracle/torch_port.Step (CPU fp32 with the
+    tensor core's TF32 operand truncation emulated), |dNCC| of the NCC kernel vs the C oracle on the step's own
+    (regA, real_B), and the number of mismatching int32 warp corner indices vs the C oracle on the step's flow."""
+    import numpy as np_
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import inputs as gi
+    from oracle import torch_port as tp, c_oracle as orc
+    from dfmir_b200 import registration_model as rm, layers, losses
+    orc.build()
+    sds = tp.random_state_dicts(ngf=64, n_blocks=9, crop=S, seed=5)
+    A = torch.from_numpy(gi.image_textured(701, 1, (S, S)))
+    Bm = torch.from_numpy(gi.image_textured(711, 1, (S, S)))
+    real_randperm = torch.randperm
+    try:
+        cnt = [100]
+        torch.randperm = gi.det_randperm(cnt)
+        tp.TF32_EMULATION = "trunc"
+        torch.set_num_threads(os.cpu_count() or 1)
+        st = tp.Step(*sds, n_blocks=9, batch_size=1, dvf_image=None)
+        want = st.step(A, Bm)
+        tp.TF32_EMULATION = None
+        opt = rm.default_options(batch_size=1, crop_size=S, load_size=S, gpu_ids=[torch.cuda.current_device()])
+        with contextlib.redirect_stdout(sys.stderr):
+            m = rm.REGISTRATIONModel(opt)
+            m.data_dependent_initialize({'A': A, 'B': Bm})
+            m.setup(opt)
+        for n, sd in zip(('G', 'F', 'R'), sds):
+            getattr(m, 'net' + n).load_state_dict(sd, strict=False)
+        cnt[0] = 100
+        m.set_input({'A': A, 'B': Bm})
+        m.optimize_parameters()
+        got = m.get_current_losses()
+    finally:
+        torch.randperm = real_randperm
+        tp.TF32_EMULATION = None
+    dl = {k: abs(got[k] - want[k]) for k in want}
+    # NCC and warp indices on the step's own tensors: CUDA kernels vs the C oracle
+    regA, realB = m.regA.detach(), m.real_B.detach()
+    ncc_gpu = float(losses.NCC_Loss('cuda', kernel_var=[9, 9])(regA, realB))
+    ncc_ref = float(orc.ncc(regA.cpu().numpy(), realB.cpu().numpy())[0])
+    flow = m.netR(m.real_A, m.real_B)[2].detach()
+    _, idx = layers.warp_indices(m.real_A, flow)
+    _, o_idx = orc.warp(m.real_A.cpu().numpy(), flow.cpu().numpy(), return_idx=True)
+    mism = int((idx.cpu().numpy() != o_idx).sum())
+    del m
+    rm_cleanup()
+    return {"workload": f"1 pair at {S}x{S}, ngf 64, 9 blocks, tcgen05 engine, eager launches; same state-dicts, inputs and patch ids",
+            "comparator": "oracle/torch_port.Step on the CPU (fp32, TF32_EMULATION=trunc: operands truncated as the tensor core does), "
+                          "pinned to the reference's own step by tests/test_oracle_nets.py; C oracle for NCC and warp indices",
+            "loss_max_abs_diff": max(dl.values()), "loss_abs_diff": dl, "losses": got, "losses_oracle": want,
+            "ncc": ncc_gpu, "ncc_oracle": ncc_ref, "ncc_abs_diff": abs(ncc_gpu - ncc_ref), "ncc_tolerance": 1e-4,
+            "warp_index_mismatches": mism, "warp_indices_compared": int(o_idx.size)}
+
+
+def gpu_library_baseline(B, S, steps=3):
+    """Informational ('the Blackwell kernel to beat'): the reference's own PyTorch composition
+    (oracle/torch_port.Step = F.conv2d / instance_norm / grid_sample / bmm with autograd, Adam) on the SAME B200 through
+    cuDNN (allow_tf32, PyTorch's default for convolutions) and ATen kernels, same batch, CUDA-event timed."""
+    from oracle import torch_port as tp
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.backends.cudnn.allow_tf32 = True
+    sds = [{k: v.to(dev) for k, v in sd.items()} for sd in tp.random_state_dicts(crop=S)]
+    A, Bm = (t.to(dev) for t in synthetic_pair(B, S, 1234))
+    st = tp.Step(*sds, n_blocks=9, batch_size=B, dvf_image=torch.zeros(B, 3, S, S, device=dev))
+    for _ in range(2):
+        st.step(A, Bm)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        st.step(A, Bm)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    del st, sds
+    rm_cleanup()
+    return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": B, "steps": steps,
+            "what": "oracle/torch_port.Step on cuda: PyTorch eager, cuDNN convolutions with allow_tf32=True, ATen grid_sample / "
+                    "instance_norm / bmm, torch.optim.Adam; the reference's schedule (feat_k recomputed, graphs built for it)",
+            "peak_mem_gib": peak}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    line = bench_2d(args, ctx)
+    workloads = {}
+    if not args.no_3d:
+        for name, (shape, B, feats, cfg) in WORKLOADS_3D.items():
+            workloads[name] = bench_3d(args, ctx, shape, B, feats, cfg)
+    ctx.close()
+    if ctx.rank != 0:
+        return
+    line["workloads"] = workloads
+    if ctx.world == 1:
+        if not args.no_parity:
+            try:
+                line["parity"] = parity_block(args.size)
+            except Exception as exc:     # the line must still be printed; a missing block reads as unmeasured
+                line["parity"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+        if not args.no_library_baseline:
+            try:
+                line["gpu_library_baseline"] = gpu_library_baseline(args.batch, args.size)
+            except Exception as exc:
+                line["gpu_library_baseline"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+                rm_cleanup()
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_2d(args.size)
+            for name, (shape, _, feats, _cfg) in WORKLOADS_3D.items():
+                if workloads.get(name) is not None:
+                    workloads[name]["cpu_baseline"] = cpu_baseline_3d(shape, feats)
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def run_ours_3d(args):
+    """One 3-D workload alone (`--workload 3d`): the top-level line is that workload's."""
+    ctx = Ctx()
+    shape = tuple(int(v) for v in args.shape3d.split(",")) if args.shape3d else (args.size3d,) * 3
+    cfg_no = 3 if shape == (160, 192, 160) else 2
+    w = bench_3d(args, ctx, shape, args.batch3d, args.features3d, cfg_no)
+    ctx.close()
+    if ctx.rank != 0:
+        return
+    line = {"metric": METRIC, "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"}
+    line.update(w)
+    if ctx.world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_3d(shape, args.features3d)
+    print(json.dumps(line))
 
 
 def main():
@@ -424,8 +616,11 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="pairs per GPU per step")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-3d", dest="no_3d", action="store_true", help="skip the 3-D workloads of the default line")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true")
+    ap.add_argument("--no-library-baseline", dest="no_library_baseline", action="store_true")
     ap.add_argument("--workload", default="2d", choices=["2d", "3d"],
-                    help="2d: BASELINE configs[1] (the headline line, default); 3d: configs[2], VoxelMorph-3D 128^3")
+                    help="2d: BASELINE configs[1] headline + the 3-D workloads under `workloads` (default); 3d: one 3-D workload alone")
     ap.add_argument("--batch3d", type=int, default=2)
     ap.add_argument("--size3d", type=int, default=128)
     ap.add_argument("--shape3d", default="", help="D,H,W of the 3-D workload (overrides --size3d), e.g. 160,192,160 for configs[3]")

@@ -72,11 +72,16 @@ def require_cuda(*tensors):
 
 
 def call(name, *args):
-    """Call a C-ABI entry point; raises DfmirError with the library's message on failure."""
+    """Call a C-ABI entry point; raises DfmirError with the library's message on failure.  The launch goes to the
+    current stream of the device that owns the first tensor argument (with that device made current for the call if
+    it is not already), so a model built with gpu_ids=[k] works whatever the caller's current device is."""
     fn = getattr(lib(), name)
     conv = []
+    dev = None
     for a in args:
         if isinstance(a, torch.Tensor) or a is None:
+            if dev is None and a is not None and a.is_cuda:
+                dev = a.device
             conv.append(_ptr(a))
         elif isinstance(a, float):
             conv.append(ctypes.c_float(a))
@@ -88,7 +93,11 @@ def call(name, *args):
             conv.append(ctypes.c_int(a))
         else:
             conv.append(a)  # already a ctypes object (c_size_t, c_longlong, ...)
-    check(fn(*conv, _stream()), name)
+    if dev is None or dev.index == torch.cuda.current_device():
+        check(fn(*conv, _stream()), name)
+    else:
+        with torch.cuda.device(dev):
+            check(fn(*conv, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), name)
 
 
 def size_t(v):

@@ -17,14 +17,15 @@ void dfmir_set_error(const char* fmt, ...) {
 void dfmir_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int dfmir_num_sms() {
-  static int n = 0;
+  // cached per device: one process may drive a model on a device other than the first one it touched
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      n = v;
-    else
-      n = 148;  // B200
+    int v = 0;
+    n = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;  // B200
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -30,25 +30,25 @@ class ConvProfile:
     including the direct 7x7 stem / head kernels)."""
 
     def __init__(self):
-        self.events = []          # (kind, start, end, flops)
+        self.events = []          # (kind, start, end, flops, operand + result bytes)
         self.calls, self.umma_calls = 0, 0
 
-    def run(self, fn, flops, kind):
+    def run(self, fn, flops, kind, nbytes=0.0):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
         e.record()
-        self.events.append((kind, s, e, flops))
+        self.events.append((kind, s, e, flops, nbytes))
         self.calls += 1
         self.umma_calls += int(kind.startswith("umma"))
 
     def by_kind(self):
-        """{kind: (total ms, total flops, calls)}"""
+        """{kind: (total ms, total flops, calls, total algorithmic bytes)}"""
         torch.cuda.synchronize()
         out = {}
-        for kind, s, e, fl in self.events:
-            ms, f, n = out.get(kind, (0.0, 0.0, 0))
-            out[kind] = (ms + s.elapsed_time(e), f + fl, n + 1)
+        for kind, s, e, fl, nb in self.events:
+            ms, f, n, b = out.get(kind, (0.0, 0.0, 0, 0.0))
+            out[kind] = (ms + s.elapsed_time(e), f + fl, n + 1, b + nb)
         return out
 
     def total(self):
@@ -59,11 +59,16 @@ class ConvProfile:
 PROFILE = None
 
 
-def _run(fn, flops, kind="simt"):
+def _run(fn, flops, kind="simt", nbytes=0.0):
     if PROFILE is None:
         fn()
     else:
-        PROFILE.run(fn, flops, kind)
+        PROFILE.run(fn, flops, kind, nbytes)
+
+
+def _nbytes(*tensors):
+    """fp32 bytes of the operands and the result of one launch (the algorithmic traffic of a convolution)"""
+    return 4.0 * sum(t.numel() for t in tensors if t is not None)
 
 
 class ConvDesc(ctypes.Structure):
@@ -183,7 +188,8 @@ class _ConvFn(torch.autograd.Function):
             dx = pending if acc else torch.empty((N, *S, Cin), dtype=x.dtype, device=x.device)
             d = _make_desc(nd, N, Cin, Cout, S, O, kernel, pad, stride, ACT_NONE, _cl_strides(dx, nd), ys)
             if acc and _lib.lib().dfmir_conv_umma_dgrad_acc_supported(ctypes.byref(d)):
-                _run(lambda: _lib.call("dfmir_conv_umma_dgrad_acc", dy, w, dx, ctypes.byref(d)), flops, "umma_dgrad")
+                _run(lambda: _lib.call("dfmir_conv_umma_dgrad_acc", dy, w, dx, ctypes.byref(d)), flops, "umma_dgrad",
+                     _nbytes(dy, w, dx, dx))
                 pending = None
             else:
                 if acc:
@@ -350,7 +356,10 @@ class _InstNormFn(torch.autograd.Function):
         ws = workspace(_lib.lib().dfmir_instnorm_workspace_bytes(N, C), x.device)
         slot = ctx.bias_slot
         dbias = None
-        if slot is not None and C % 4 == 0 and dy.data_ptr() % 16 == 0:
+        # the bias by-product exists on the 128-bit kernels only (csrc/norm_resample.cu in_v4_ok)
+        v4 = (C % 4 == 0 and C // 4 <= 256 and 256 % (C // 4) == 0 and N <= 65535
+              and all(t is None or t.data_ptr() % 16 == 0 for t in (dy, x, dx, dres, stats)))
+        if slot is not None and v4:
             dbias = torch.empty(C, dtype=x.dtype, device=x.device)
         _lib.call("dfmir_instnorm_bwd_bias", dy, x, stats, dx, dres, dbias, ws, _lib.size_t(ws.numel()), N, H, W, C, relu,
                   out_pad, res_pad)

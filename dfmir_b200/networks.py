@@ -304,6 +304,7 @@ class PatchSampleF(nn.Module):
         self.init_type = init_type
         self.init_gain = init_gain
         self.gpu_ids = gpu_ids
+        self.generator = None       # optional torch.Generator for the patch ids (REGISTRATIONModel.parallelize)
 
     def create_mlp(self, feats):
         for mlp_id, feat in enumerate(feats):
@@ -325,7 +326,8 @@ class PatchSampleF(nn.Module):
             if patch_ids is not None:
                 patch_id = patch_ids[feat_id]
             else:
-                patch_id = torch.randperm(H * W, device=feat.device)
+                patch_id = torch.randperm(H * W, device=feat.device, generator=self.generator) \
+                    if self.generator is not None else torch.randperm(H * W, device=feat.device)
                 patch_id = patch_id[:int(min(num_patches, patch_id.shape[0]))]
             x_sample = Fn.gather_patches(feat, patch_id)          # (B*P, C)
             if self.use_mlp:

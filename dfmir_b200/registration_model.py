@@ -81,7 +81,8 @@ def global_mask_scale(msum, world):
     """Factor that turns a rank-local masked mean  S_r / M_r  into this rank's share of the global-batch
     masked mean  sum_r S_r / sum_r M_r  (reference registration_model.py:262-263 divides by the mask sum of
     the WHOLE batch): after gradients are averaged over the `world` ranks,
-    mean_r[(S_r / M_r) * (M_r * world / sum M)] = sum S / sum M.  One scalar all-reduce."""
+    mean_r[(S_r / M_r) * (M_r * world / sum M)] = sum S / sum M.  `msum` may hold several mask sums (one
+    entry per masked term of the step): ONE small all-reduce serves them all."""
     import torch.distributed as dist
     total = msum.clone()
     dist.all_reduce(total)
@@ -104,6 +105,7 @@ class BaseModel:
         self.loss_names, self.model_names, self.visual_names, self.optimizers, self.image_paths = [], [], [], [], []
         self.metric = 0
         self._flat_grad = None
+        self._buckets, self._bucket_work, self._overlap = [], [], False
         self._world = 1
         self._graph = None
         self.graph_launches_per_step = 0
@@ -116,40 +118,107 @@ class BaseModel:
         self.print_networks(opt.verbose)
 
     def parallelize(self):
-        """One process per GPU (torchrun): replicate weights from rank 0 once, then average gradients
-        with a single NCCL all-reduce per step over a flat buffer that every `.grad` is a view of."""
+        """One process per GPU (torchrun): replicate weights from rank 0 once, then average gradients over NCCL.
+        Every `.grad` is a view of one flat buffer laid out in the order the backward pass finishes the
+        parameters: [R, F | G decoder half | G encoder half].  Each bucket's all-reduce (ReduceOp.AVG) is
+        issued from a post-accumulate hook as soon as its last gradient is written, so the collectives of
+        the first buckets overlap the rest of the backward pass; optimize_parameters() waits for them
+        before the Adam steps.  The global RNG is left alone (each rank keeps its own data order):
+        the patch ids PatchSampleF draws come from a dedicated generator seeded identically on all ranks
+        (the reference draws one permutation per layer for the whole DataParallel batch, networks.py:609)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
         self._world = dist.get_world_size()
-        params = []
         for name in self.model_names:
             net = getattr(self, 'net' + name)
             for t in list(net.parameters()) + list(net.buffers()):
                 dist.broadcast(t.data, src=0)
-            params += [p for p in net.parameters() if p.requires_grad]
+        groups = self._grad_bucket_groups()
+        params = [p for g in groups for p in g]
         total = sum(p.numel() for p in params)
-        self._flat_grad = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        dev = params[0].device
+        self._flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._buckets, self._bucket_work, self._bucket_hooks = [], [], []
         off = 0
-        for p in params:
-            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        # identical patch ids on every rank (networks.py:609 draws one permutation per layer)
-        seed = torch.randint(0, 2 ** 31 - 1, (1,), device=params[0].device)
+        for g in groups:
+            start = off
+            for p in g:
+                p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            if off > start:
+                self._buckets.append([self._flat_grad[start:off], len(g), 0, False])   # view, #params, #ready, reduced
+        overlap = os.environ.get("DFMIR_OVERLAP_ALLREDUCE", "1") != "0"
+        if overlap:
+            for bi, g in enumerate(groups):
+                for p in g:
+                    self._bucket_hooks.append(p.register_post_accumulate_grad_hook(self._make_bucket_hook(bi)))
+        self._overlap = overlap
+        seed = torch.randint(0, 2 ** 31 - 1, (1,), device=dev)
         dist.broadcast(seed, src=0)
-        torch.manual_seed(int(seed.item()))
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(seed.item()))
+        netF = getattr(self, 'netF', None)
+        if netF is not None:
+            netF.generator = gen
+
+    def _grad_bucket_groups(self):
+        """Parameters grouped by when the backward pass completes their gradients (see parallelize)."""
+        def trainable(net):
+            return [p for p in net.parameters() if p.requires_grad]
+        early, dec, enc = [], [], []
+        for name in self.model_names:
+            net = getattr(self, 'net' + name)
+            if name != 'G' or not hasattr(net, 'model'):
+                early += trainable(net)
+                continue
+            # modules up to the last feature tap are shared by the encoder passes: their packed-weight
+            # gradient is complete only when the full pass has been walked back to them
+            last_tap = max(getattr(self, 'nce_layers', [0]))
+            for i, m in enumerate(net.model):
+                (enc if i <= last_tap else dec).extend(trainable(m))
+        return [g for g in (early, dec, enc) if g]
+
+    def _make_bucket_hook(self, bi):
+        def hook(_param):
+            b = self._buckets[bi]
+            b[2] += 1
+            if b[2] == b[1] and not b[3]:
+                b[3] = True
+                self._bucket_work.append(self._allreduce_mean(b[0], True))
+        return hook
+
+    def _allreduce_mean(self, t, async_op):
+        """Mean over ranks: NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and
+        _sync_grads scales afterwards."""
+        import torch.distributed as dist
+        native = dist.get_backend() == 'nccl'
+        self._scale_after = not native
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG if native else dist.ReduceOp.SUM, async_op=async_op)
 
     def _zero_grads(self):
         if self._flat_grad is not None:
             self._flat_grad.zero_()
+            for b in self._buckets:
+                b[2], b[3] = 0, False
         else:
             for opt_ in self.optimizers:
                 opt_.zero_grad()
 
     def _sync_grads(self):
-        if self._flat_grad is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self._flat_grad)
+        if self._flat_grad is None:
+            return
+        if self._overlap:
+            for b in self._buckets:
+                if not b[3]:            # a parameter of this bucket received no gradient during the backward pass
+                    self._bucket_work.append(self._allreduce_mean(b[0], True))
+                b[2], b[3] = 0, False
+            for w in self._bucket_work:
+                w.wait()
+            self._bucket_work = []
+        else:
+            self._allreduce_mean(self._flat_grad, False)
+        if getattr(self, '_scale_after', False):
             self._flat_grad.mul_(1.0 / self._world)
 
     def data_dependent_initialize(self, data):
@@ -171,13 +240,17 @@ class BaseModel:
         return self.image_paths
 
     def update_learning_rate(self):
-        self._graph = None          # a captured step has the old learning rate baked in
+        # with opt.cuda_graph the learning rate is a device tensor the captured Adam kernels read: the
+        # schedulers fill it in place and the graph stays valid; a python-float rate is baked into a capture
+        if self._graph is not None and not all(torch.is_tensor(g['lr']) for o in self.optimizers for g in o.param_groups):
+            print('dfmir_b200: learning rate is not a device tensor; dropping the captured step (eager launches from here on)')
+            self._graph = None
         for scheduler in self.schedulers:
             if self.opt.lr_policy == 'plateau':
                 scheduler.step(self.metric)
             else:
                 scheduler.step()
-        print('learning rate = %.7f' % self.optimizers[0].param_groups[0]['lr'])
+        print('learning rate = %.7f' % float(self.optimizers[0].param_groups[0]['lr']))
 
     def get_current_visuals(self):
         return OrderedDict((name, getattr(self, name)) for name in self.visual_names)
@@ -186,22 +259,41 @@ class BaseModel:
         return OrderedDict((name, float(getattr(self, 'loss_' + name).detach() if torch.is_tensor(getattr(self, 'loss_' + name)) else getattr(self, 'loss_' + name))) for name in self.loss_names)
 
     def save_networks(self, epoch):
+        """`<epoch>_net_<name>.pth` per network with the reference's state-dict keys (base_model.py:164-180), plus
+        `<epoch>_optim.pth` with the optimiser / scheduler state the reference omits, so that a resumed
+        run continues Adam's moments and the learning-rate schedule instead of restarting them."""
         os.makedirs(self.save_dir, exist_ok=True)
         for name in self.model_names:
             net = getattr(self, 'net' + name)
             sd = OrderedDict((k, v.detach().cpu()) for k, v in net.state_dict().items())
             torch.save(sd, os.path.join(self.save_dir, '%s_net_%s.pth' % (epoch, name)))
+        if self.isTrain and self.optimizers:
+            torch.save({'optimizers': [o.state_dict() for o in self.optimizers],
+                        'schedulers': [s.state_dict() for s in getattr(self, 'schedulers', [])]},
+                       os.path.join(self.save_dir, '%s_optim.pth' % epoch))
 
     def load_networks(self, epoch):
+        load_dir = os.path.join(self.opt.checkpoints_dir, self.opt.pretrained_name) \
+            if self.opt.isTrain and self.opt.pretrained_name is not None else self.save_dir
         for name in self.model_names:
-            load_dir = os.path.join(self.opt.checkpoints_dir, self.opt.pretrained_name) \
-                if self.opt.isTrain and self.opt.pretrained_name is not None else self.save_dir
             load_path = os.path.join(load_dir, '%s_net_%s.pth' % (epoch, name))
             print('loading the model from %s' % load_path)
             state_dict = torch.load(load_path, map_location=str(self.device))
             if hasattr(state_dict, '_metadata'):
                 del state_dict._metadata
             getattr(self, 'net' + name).load_state_dict(state_dict)
+        optim_path = os.path.join(load_dir, '%s_optim.pth' % epoch)
+        if self.isTrain and os.path.exists(optim_path):        # absent in checkpoints written by the reference
+            st = torch.load(optim_path, map_location=str(self.device))
+            for o, sd in zip(self.optimizers, st['optimizers']):
+                lrs = [g['lr'] for g in o.param_groups]
+                o.load_state_dict(sd)
+                for g, lr in zip(o.param_groups, lrs):         # keep the device-tensor learning rate of a captured step
+                    if torch.is_tensor(lr):
+                        lr.fill_(float(g['lr']))
+                        g['lr'] = lr
+            for s, sd in zip(getattr(self, 'schedulers', []), st['schedulers']):
+                s.load_state_dict(sd)
 
     def print_networks(self, verbose):
         print('---------- Networks initialized -------------')
@@ -239,11 +331,18 @@ class REGISTRATIONModel(BaseModel):
         if self.isTrain:
             self.criterionNCE = [PatchNCELoss(opt).to(self.device) for _ in self.nce_layers]
             self.criterionNCC = losses.NCC_Loss(self.device, name='ncc', kernel_var=[9, 9], kernel_type='mean')
-            cap = bool(getattr(opt, 'cuda_graph', False))        # step counters on the device, so that Adam can be graph-captured
-            self.optimizer_G = torch.optim.Adam(self.netG.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2), capturable=cap)
-            self.optimizer_R = torch.optim.Adam(self.netR.parameters(), lr=opt.lr, betas=(opt.beta1, opt.beta2), capturable=cap)
+            self.optimizer_G = self._make_adam(self.netG.parameters())
+            self.optimizer_R = self._make_adam(self.netR.parameters())
             self.optimizers.append(self.optimizer_G)
             self.optimizers.append(self.optimizer_R)
+
+    def _make_adam(self, params):
+        """torch.optim.Adam with the reference's hyper-parameters (registration_model.py:114-115,135).  With
+        opt.cuda_graph the step counters AND the learning rate live on the device (capturable Adam, tensor lr): a
+        captured step keeps following the schedulers, which fill the tensor in place."""
+        cap = bool(getattr(self.opt, 'cuda_graph', False))
+        lr = torch.tensor(float(self.opt.lr), dtype=torch.float32, device=self.device) if cap else self.opt.lr
+        return torch.optim.Adam(params, lr=lr, betas=(self.opt.beta1, self.opt.beta2), capturable=cap)
 
     def data_dependent_initialize(self, data):
         self.set_input(data)
@@ -254,24 +353,26 @@ class REGISTRATIONModel(BaseModel):
         if self.opt.isTrain:
             self.compute_G_loss().backward()
             if self.opt.lambda_NCE > 0.0:
-                self.optimizer_F = torch.optim.Adam(self.netF.parameters(), lr=self.opt.lr,
-                                                    betas=(self.opt.beta1, self.opt.beta2),
-                                                    capturable=bool(getattr(self.opt, 'cuda_graph', False)))
+                self.optimizer_F = self._make_adam(self.netF.parameters())
                 self.optimizers.append(self.optimizer_F)
 
     def optimize_parameters(self):
         if self._graph is not None:
             self._graph.replay()
+            # the captured Adam kernels update the parameters in place without bumping their version counters:
+            # kernel-layout weight copies cached by a later no-grad forward (test(), visuals) must not survive
+            from . import functional as Fn, umma
+            Fn._pack_cache.clear()
+            umma._kmajor_cache.clear()
             return
         self._step()
 
     def capture_step(self):
         """Capture one training step (forward, losses, backward, gradient all-reduce, the three Adam steps) into a CUDA
         graph; optimize_parameters() then replays it: ~2.3 k kernel launches per step stop costing host time
-        (SURVEY 8f N1).  Needs opt.cuda_graph=True at construction (capturable Adam), a few eager steps on inputs of
-        the final shape first (lazy initialisation, allocator warm-up), and set_input() afterwards copies into the
-        captured input buffers.  update_learning_rate() drops the graph (the learning rate is baked into it); call
-        capture_step() again after it."""
+        (SURVEY 8f N1).  Needs opt.cuda_graph=True at construction (capturable Adam with the learning rate held in a
+        device tensor, so update_learning_rate() keeps the graph), a few eager steps on inputs of the final shape first
+        (lazy initialisation, allocator warm-up), and set_input() afterwards copies into the captured input buffers."""
         if not getattr(self.opt, 'cuda_graph', False):
             raise _lib.DfmirError("capture_step: construct the model with opt.cuda_graph=True (capturable Adam)")
         self._graph = None
@@ -290,6 +391,9 @@ class REGISTRATIONModel(BaseModel):
         self._release_tapes()
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
+        gen = getattr(getattr(self, 'netF', None), 'generator', None)
+        if gen is not None:             # patch ids drawn from the rank-shared generator advance with every replay
+            graph.register_generator_state(gen)
         n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
             self._step()
@@ -322,8 +426,8 @@ class REGISTRATIONModel(BaseModel):
         self.loss_G = self.compute_G_loss()
         # masked L1 terms: mask = (u > -0.95) | (v > -0.95) built inside the loss kernel (:160-161)
         self.loss_local = self.calculate_NCE_loss(self.real_B, self.regA) * 0.25
-        l1_a = self._masked_l1(self.registered, self.real_B, self.real_B, self.registered)
-        l1_b = self._masked_l1(self.idt_B, self.registered, self.idt_B, self.registered)
+        l1_a, l1_b = self._masked_l1_pair((self.registered, self.real_B, self.real_B, self.registered),
+                                          (self.idt_B, self.registered, self.idt_B, self.registered))
         self.loss_R = l1_a * 1.0 + l1_b * 1.0 + self.loss_local * 1.0
         self.loss_smooth = smooothing_loss(pos_flow) * 0.20
         all_G_loss = self.loss_R + self.loss_G + self.loss_smooth
@@ -334,11 +438,13 @@ class REGISTRATIONModel(BaseModel):
         if self.opt.netF == 'mlp_sample':
             self.optimizer_F.step()
 
-    def _masked_l1(self, src, tgt, mu, mv):
-        loss, msum = losses.l1_threshold_masked(src, tgt, mu, mv, thr=-0.95, return_mask_sum=True)
+    def _masked_l1_pair(self, *terms):
+        """The step's masked-L1 terms; across ranks their mask sums are made global by ONE all-reduce."""
+        out = [losses.l1_threshold_masked(src, tgt, mu, mv, thr=-0.95, return_mask_sum=True) for src, tgt, mu, mv in terms]
         if self._world > 1:
-            loss = loss * global_mask_scale(msum.detach(), self._world)
-        return loss
+            scale = global_mask_scale(torch.stack([m.detach() for _, m in out]), self._world)
+            return [loss * scale[i] for i, (loss, _) in enumerate(out)]
+        return [loss for loss, _ in out]
 
     def set_input(self, input):
         AtoB = self.opt.direction == 'AtoB'
@@ -402,6 +508,7 @@ class REGISTRATIONModel(BaseModel):
             if not mlp_ready:
                 self.netF.create_mlp(feat_k)
             feat_k_pool, sample_ids = self.netF(feat_k, self.opt.num_patches, patch_ids)
+        self._last_patch_ids = sample_ids           # observable by tests (graph replays must draw fresh ids)
         feat_q_pool, _ = self.netF(feat_q, self.opt.num_patches, sample_ids)
         total_nce_loss = 0.0
         for f_q, f_k, crit, nce_layer in zip(feat_q_pool, feat_k_pool, self.criterionNCE, self.nce_layers):

@@ -17,9 +17,13 @@ def supported(d, dgrad=False):
     return bool(_lib.lib().dfmir_conv_umma_supported(ctypes.byref(d), int(dgrad)))
 
 
-def _run(fn, flops, kind):
+def _run(fn, flops, kind, nbytes=0.0):
     from . import functional as Fn
-    Fn._run(fn, flops, kind)
+    Fn._run(fn, flops, kind, nbytes)
+
+
+def _nbytes(*tensors):
+    return 4.0 * sum(t.numel() for t in tensors if t is not None)
 
 
 _kmajor_cache = {}
@@ -42,16 +46,16 @@ def _kmajor(w):
 
 def conv_fwd(x, w, bias, y, d, flops=0.0):
     wk = _kmajor(w)
-    _run(lambda: _lib.call("dfmir_conv_umma_fwd", x, wk, bias, y, ctypes.byref(d)), flops, "umma_fwd")
+    _run(lambda: _lib.call("dfmir_conv_umma_fwd", x, wk, bias, y, ctypes.byref(d)), flops, "umma_fwd", _nbytes(x, wk, y))
 
 
 def conv_dgrad(dy, w, dx, d, flops=0.0):
     # [tap][Cin][Cout] is K-major for this product
-    _run(lambda: _lib.call("dfmir_conv_umma_dgrad", dy, w, dx, ctypes.byref(d)), flops, "umma_dgrad")
+    _run(lambda: _lib.call("dfmir_conv_umma_dgrad", dy, w, dx, ctypes.byref(d)), flops, "umma_dgrad", _nbytes(dy, w, dx))
 
 
 def conv_wgrad(x, dy, dw, db, d, flops=0.0):
     if _lib.lib().dfmir_conv_umma_wgrad_supported(ctypes.byref(d)):
-        _run(lambda: _lib.call("dfmir_conv_umma_wgrad", x, dy, dw, db, ctypes.byref(d)), flops, "umma_wgrad")
+        _run(lambda: _lib.call("dfmir_conv_umma_wgrad", x, dy, dw, db, ctypes.byref(d)), flops, "umma_wgrad", _nbytes(x, dy, dw))
     else:
         _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops, "simt")

@@ -14,6 +14,9 @@ Follows (paths relative to the reference repo):
     vec_int / resize   models/voxelmorph/torchvoxelmorph/layers.py:64-68, 85-97
     vxm_dense          models/voxelmorph/torchvoxelmorph/networks.py:88-106, 1102-1145
     step               models/registration_model.py:138-171, 213-263
+    ncc_loss / grad_loss  util/losses.py:183-261 (box filters as dense convolutions, like the reference), :81-130
+    Step3D             VxmDense-3D + NCC_Loss + Grad_Loss forward / backward + Adam: the 3-D workloads of BASELINE
+                       configs[2..4] (BASELINE.md section 2 times exactly this composition of the reference)
 """
 import numpy as np
 import torch
@@ -219,6 +222,96 @@ def smoothing(y):
     dy = torch.abs(y[:, :, 1:, :] - y[:, :, :-1, :])
     dx = torch.abs(y[:, :, :, 1:] - y[:, :, :, :-1])
     return (torch.mean(dx * dx) + torch.mean(dy * dy)) / 2.0
+
+
+def ncc_loss(prediction, target, win=9, eps=1e-5, mask=None):
+    """NCC_Loss.forward with the 'mean' kernel: five box sums as dense conv{2,3}d with a ones filter, zero padding
+    win // 2; cc = cross^2 / (I_var * J_var + eps); -sqrt(mean(cc))  (util/losses.py:183-261)."""
+    nd = prediction.dim() - 2
+    conv = getattr(F, 'conv%dd' % nd)
+    filt = torch.ones([1, 1] + [win] * nd, dtype=prediction.dtype, device=prediction.device)
+    pad = win // 2
+    I, J = prediction, target
+    I_sum, J_sum = conv(I, filt, padding=pad), conv(J, filt, padding=pad)
+    I2_sum, J2_sum, IJ_sum = conv(I * I, filt, padding=pad), conv(J * J, filt, padding=pad), conv(I * J, filt, padding=pad)
+    win_size = torch.sum(filt)
+    u_I, u_J = I_sum / win_size, J_sum / win_size
+    cross = IJ_sum - u_J * I_sum - u_I * J_sum + u_I * u_J * win_size
+    I_var = I2_sum - 2 * u_I * I_sum + u_I * u_I * win_size
+    J_var = J2_sum - 2 * u_J * J_sum + u_J * u_J * win_size
+    cc = cross * cross / (I_var * J_var + eps)
+    if mask is None:
+        return -1.0 * torch.sqrt(torch.mean(cc))
+    if torch.sum(mask) == 0:
+        return torch.tensor(0)
+    return -1.0 * torch.sqrt((1 / torch.sum(mask)) * torch.sum(cc * mask))
+
+
+def grad_loss(prediction, penalty='l2'):
+    """Grad_Loss(dim = nd): mean |forward difference|^p along each spatial axis, averaged over the axes
+    (util/losses.py:81-130)."""
+    nd = prediction.dim() - 2
+    total = 0.0
+    for ax in range(2, 2 + nd):
+        n = prediction.shape[ax]
+        d = torch.abs(prediction.narrow(ax, 1, n - 1) - prediction.narrow(ax, 0, n - 1))
+        total = total + torch.mean(d * d if penalty == 'l2' else d)
+    return total / float(nd)
+
+
+def random_state_dict_r3d(feats, seed=0):
+    """Random-initialised VxmDense-3D weights (PyTorch conv defaults + N(0, 1e-5) flow head) for timing runs."""
+    g = torch.Generator().manual_seed(seed)
+    enc, dec = feats
+
+    def kaiming_u(shape):
+        bound = (1.0 / (shape[1] * int(np.prod(shape[2:])))) ** 0.5
+        return (torch.rand(shape, generator=g) * 2 - 1) * bound
+    R, prev = {}, 2
+    for i, nf in enumerate(enc):
+        R[f'unet_model.downarm.{i}.main.weight'] = kaiming_u((nf, prev, 3, 3, 3)); R[f'unet_model.downarm.{i}.main.bias'] = torch.zeros(nf)
+        prev = nf
+    hist = list(reversed(enc))
+    for i, nf in enumerate(dec[:len(enc)]):
+        ch = prev + hist[i] if i > 0 else prev
+        R[f'unet_model.uparm.{i}.main.weight'] = kaiming_u((nf, ch, 3, 3, 3)); R[f'unet_model.uparm.{i}.main.bias'] = torch.zeros(nf)
+        prev = nf
+    prev += 2
+    for i, nf in enumerate(dec[len(enc):]):
+        R[f'unet_model.extras.{i}.main.weight'] = kaiming_u((nf, prev, 3, 3, 3)); R[f'unet_model.extras.{i}.main.bias'] = torch.zeros(nf)
+        prev = nf
+    R['flow.weight'] = torch.randn((3, prev, 3, 3, 3), generator=g) * 1e-5
+    R['flow.bias'] = torch.zeros(3)
+    return R
+
+
+class Step3D:
+    """One 3-D registration training step the way the reference composes it:
+    VxmDense(bidir=False).forward -> NCC_Loss([win]^3)(y_source, target) + lam * Grad_Loss(dim=3)(flow) -> backward -> Adam."""
+
+    def __init__(self, sdR, feats, int_steps=7, win=9, lam=0.02, lr=2e-4, betas=(0.5, 0.999)):
+        self.P = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith('.grid')) for k, v in sdR.items()}
+        self.levels = (len(feats[0]), len(feats[1]))
+        self.int_steps, self.win, self.lam = int_steps, win, lam
+        self.opt = torch.optim.Adam([v for v in self.P.values() if v.requires_grad], lr=lr, betas=betas)
+        self.losses = {}
+
+    def forward(self, source, target):
+        x = unet(torch.cat([source, target], dim=1), self.P, *self.levels)
+        pos = resize_transform(F.conv3d(x, self.P['flow.weight'], self.P['flow.bias'], padding=1), 2)
+        pos = resize_transform(vec_int(pos, self.int_steps), 0.5)
+        return spatial_transform(source, pos), pos
+
+    def step(self, source, target):
+        self.opt.zero_grad()
+        y, flow = self.forward(source, target)
+        ncc = ncc_loss(y, target, self.win)
+        grad = grad_loss(flow)
+        (ncc + self.lam * grad).backward()
+        self.opt.step()
+        self.losses = {'ncc': float(ncc.detach()), 'grad': float(grad.detach())}
+        self.y, self.flow = y.detach(), flow.detach()
+        return self.losses
 
 
 class Step:

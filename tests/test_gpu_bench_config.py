@@ -1,0 +1,174 @@
+"""The BENCHMARKED configuration (BASELINE configs[1]: 2-D 256x256, ngf 64, 9 ResnetBlocks, default = tcgen05
+engine) pinned end to end to the oracle: one REGISTRATIONModel.optimize_parameters against
+oracle.torch_port.Step (the CPU restatement pinned to the reference's own step, tests/test_oracle_nets.py) on the
+same state-dicts, inputs and patch ids — eager launches AND the captured CUDA graph.
+
+Comparators:
+  tight  torch_port with TF32_EMULATION="trunc" (fp32 accumulate; the operand truncation the tensor core applies):
+         the six logged losses within 2e-3 relative, visuals within 5e-3;
+  class  torch_port in float64: every weight gradient no further from float64 than 2x the emulated run's own
+         distance (+ 2e-3 of the tensor's scale), i.e. the tcgen05 step is in the error class of TF32 arithmetic
+         (what cuDNN gives the reference on a GPU) and not worse.
+Graph replay vs eager on equal parameters / patch ids: every forward quantity (six losses, five visuals)
+bit-identical; gradients equal to accumulation-order noise (the split-K weight-gradient kernels reduce with
+red.global.add, whose order is not fixed).
+"""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import inputs as gi
+
+pytestmark = pytest.mark.gpu
+
+S = 256
+SIZES = [(S + 6) ** 2, S * S, (S // 2) ** 2, (S // 4) ** 2, (S // 4) ** 2]     # H*W of the five tapped layers
+LOSSES = ('G', 'NCE', 'R', 'smooth', 'local', 'NCE_Y')
+VISUALS = ('fake_B', 'idt_B', 'registered', 'regA')
+
+
+class CyclicRandperm:
+    """Stand-in for torch.randperm: call k of a step (k = 0..14: three NCE terms x five layers) returns the
+    permutation inputs.det_randperm gives the oracle for counter base + k + 1, as a device tensor created once
+    (no host copy inside a graph capture); every step draws the same ids."""
+
+    def __init__(self, base=100, period=15):
+        self.base, self.period, self.k, self.cache = base, period, 0, {}
+
+    def __call__(self, n, device=None, **kw):
+        key = (self.k % self.period, int(n))
+        self.k += 1
+        if key not in self.cache:
+            self.cache[key] = torch.from_numpy(np.random.RandomState(9000 + self.base + key[0] + 1).permutation(int(n))).to(device or 'cpu')
+        return self.cache[key]
+
+
+def build(B, sds, cuda_graph):
+    from dfmir_b200 import registration_model as rm
+    opt = rm.default_options(batch_size=B, crop_size=S, load_size=S, gpu_ids=[0], cuda_graph=cuda_graph)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = rm.REGISTRATIONModel(opt)
+        m.data_dependent_initialize({'A': torch.zeros(B, 1, S, S), 'B': torch.zeros(B, 1, S, S)})
+        m.setup(opt)
+    load(m, sds)
+    return m
+
+
+def load(m, sds):
+    for n, sd in zip(('G', 'F', 'R'), sds):
+        res = getattr(m, 'net' + n).load_state_dict(sd, strict=False)
+        assert not res.unexpected_keys and all(k.endswith(('.grid', '.filt')) for k in res.missing_keys), res
+    for o in m.optimizers:                     # in place: a captured graph keeps reading these tensors
+        for st in o.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+
+
+def oracle_step(sds, A, Bm, B, dtype, emulate):
+    from oracle import torch_port as tp
+    cnt = [100]
+    tp.TF32_EMULATION = emulate
+    real_randperm = torch.randperm
+    torch.randperm = gi.det_randperm(cnt)
+    try:
+        st = tp.Step(*[{k: v.to(dtype) if v.is_floating_point() else v for k, v in sd.items()} for sd in sds],
+                     n_blocks=9, batch_size=B, dvf_image=None)
+        losses = st.step(A.to(dtype), Bm.to(dtype))
+    finally:
+        tp.TF32_EMULATION = None
+        torch.randperm = real_randperm
+    grads = {n: {k: v.grad.double() for k, v in st.P[n].items() if v.grad is not None} for n in st.P}
+    vis = {k: v.detach().double() for k, v in st.visuals.items() if v is not None}
+    return losses, grads, vis
+
+
+def snapshot(m):
+    losses = m.get_current_losses()
+    vis = {k: getattr(m, k).detach().clone() for k in VISUALS}
+    grads = {n: {k: p.grad.detach().clone() for k, p in getattr(m, 'net' + n).named_parameters()} for n in ('G', 'F', 'R')}
+    return losses, vis, grads
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_benchmarked_config_step_vs_oracle(B, monkeypatch):
+    from oracle import torch_port as tp
+    import dfmir_b200.functional as Fn
+    sds = tp.random_state_dicts(ngf=64, n_blocks=9, crop=S, seed=5)
+    A = torch.from_numpy(gi.image_textured(700 + B, B, (S, S)))
+    Bm = torch.from_numpy(gi.image_textured(710 + B, B, (S, S)))
+    o64 = oracle_step(sds, A, Bm, B, torch.float64, None)
+    oem = oracle_step(sds, A, Bm, B, torch.float32, "trunc")
+
+    rp = CyclicRandperm()
+    monkeypatch.setattr(torch, "randperm", rp)
+    assert Fn.CONV_ENGINE == "auto"
+    # ---- eager launches
+    m = build(B, sds, cuda_graph=False)
+    prof = Fn.ConvProfile()
+    Fn.PROFILE = prof
+    try:
+        rp.k = 0
+        m.set_input({'A': A, 'B': Bm})
+        m.optimize_parameters()
+    finally:
+        Fn.PROFILE = None
+    assert prof.umma_calls > 200, prof.umma_calls         # the generator's convolutions ran on the tcgen05 engine
+    e_losses, e_vis, e_grads = snapshot(m)
+    for k in LOSSES:
+        ref = oem[0][k]
+        assert abs(e_losses[k] - ref) <= 2e-3 * max(1.0, abs(ref)), ("tight", k, e_losses[k], ref)
+        assert abs(e_losses[k] - o64[0][k]) <= 1e-2 * max(1.0, abs(o64[0][k])), ("float64", k, e_losses[k], o64[0][k])
+    for k in VISUALS:
+        err = float((e_vis[k].cpu().double() - oem[2][k]).abs().max())
+        assert err <= 5e-3, (k, err)
+    worst = 0.0
+    for n in ('G', 'F', 'R'):
+        for k, g in e_grads[n].items():
+            if not k.endswith("weight"):
+                continue          # biases: exactly-zero true gradients in front of the instance norms (inputs.grad_tolerance)
+            ref = o64[1][n][k]
+            sc = float(ref.abs().max())
+            if sc < 1e-12:
+                continue
+            e_tc = float((g.cpu().double() - ref).abs().max()) / sc
+            e_emu = float((oem[1][n][k] - ref).abs().max()) / sc
+            worst = max(worst, e_tc / (2.0 * e_emu + 2e-3))
+            assert e_tc <= 2.0 * e_emu + 2e-3, (n, k, e_tc, e_emu)
+            gd = g.cpu().double()
+            cos = float((gd * ref).sum() / (gd.norm() * ref.norm() + 1e-300))
+            assert cos >= 0.98, (n, k, cos)
+    print(f"B={B}: worst gradient error / (2 x emulation error + 2e-3) = {worst:.3f}")
+    del m
+
+    # ---- the same step as a captured CUDA graph: parameters, optimizer state and patch ids reset to the same start
+    mg = build(B, sds, cuda_graph=True)
+    rp.k = 0
+    mg.set_input({'A': A, 'B': Bm})
+    mg.optimize_parameters()                   # eager steps of the capturable configuration (allocator warm-up)
+    rp.k = 0
+    mg.capture_step()
+    assert rp.k % 15 == 0
+    load(mg, sds)
+    mg.set_input({'A': A, 'B': Bm})
+    mg.optimize_parameters()
+    assert mg._graph is not None
+    g_losses, g_vis, g_grads = snapshot(mg)
+    for k in LOSSES:
+        assert g_losses[k] == e_losses[k], ("graph vs eager", k, g_losses[k], e_losses[k])
+    for k in VISUALS:
+        assert torch.equal(g_vis[k], e_vis[k]), ("graph vs eager", k)
+    for n in ('G', 'F', 'R'):
+        for k, g in g_grads[n].items():
+            if n == 'G' and k.endswith('.bias'):
+                continue      # true gradient zero in front of an instance norm: what is stored is summation-order noise
+            sc = float(e_grads[n][k].abs().max())
+            assert float((g - e_grads[n][k]).abs().max()) <= 1e-4 * sc + 1e-12, ("graph vs eager gradient", n, k)
+    # a second replay from the same start reproduces the forward bit for bit
+    load(mg, sds)
+    mg.optimize_parameters()
+    again = mg.get_current_losses()
+    assert all(again[k] == g_losses[k] for k in LOSSES), (again, g_losses)

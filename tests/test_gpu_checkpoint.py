@@ -1,0 +1,84 @@
+"""Checkpoint format: save_networks / load_networks of the BaseModel mirror
+(models/base_model.py:164-224) and LoadableModel.save / load of the VoxelMorph mirror (vxm/modelio.py:57-76) round-trip
+bit for bit, the `.grid` buffers are rebuilt rather than stored, files carry exactly the reference's state-dict keys,
+and optimiser / scheduler state (which the reference omits) is saved alongside so that training resumes identically."""
+import contextlib
+import io
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def make(tmp, name, cuda_graph=False):
+    import bench
+    from dfmir_b200 import registration_model as rm
+    opt = rm.default_options(batch_size=2, ngf=8, crop_size=64, load_size=64, netF_nc=32, num_patches=64, gpu_ids=[0],
+                             checkpoints_dir=str(tmp), name=name, cuda_graph=cuda_graph)
+    torch.manual_seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = rm.REGISTRATIONModel(opt)
+        A, B = bench.synthetic_pair(2, 64, 11)
+        data = {"A": A, "B": B}
+        model.data_dependent_initialize(data)
+        model.setup(opt)
+    model.set_input(data)
+    return model, data
+
+
+def test_save_load_networks_round_trip(tmp_path):
+    model, data = make(tmp_path, "a")
+    for _ in range(2):
+        model.optimize_parameters()
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.save_networks("latest")
+    files = sorted(os.listdir(os.path.join(tmp_path, "a")))
+    assert files == ["latest_net_F.pth", "latest_net_G.pth", "latest_net_R.pth", "latest_optim.pth"], files
+    sdG = torch.load(os.path.join(tmp_path, "a", "latest_net_G.pth"))
+    assert "model.1.weight" in sdG and "model.12.conv_block.1.weight" in sdG and "model.7.filt" in sdG
+    sdR = torch.load(os.path.join(tmp_path, "a", "latest_net_R.pth"))
+    assert "transformer.grid" in sdR and "integrate.transformer.grid" in sdR and "flow.weight" in sdR
+
+    other, _ = make(tmp_path, "a")
+    for p in other.netG.parameters():
+        p.data.add_(1.0)                           # make sure the load really overwrites
+    other.opt.epoch = "latest"
+    with contextlib.redirect_stdout(io.StringIO()):
+        other.load_networks("latest")
+    for n in ("G", "F", "R"):
+        a, b = getattr(model, "net" + n).state_dict(), getattr(other, "net" + n).state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), (n, k)
+    # optimiser + scheduler state: the resumed model takes the same next step as the original
+    torch.manual_seed(5)                           # same patch ids for both
+    model.optimize_parameters()
+    other.set_input(data)
+    torch.manual_seed(5)
+    other.optimize_parameters()
+    for n in ("G", "F", "R"):
+        want, got = getattr(model, "net" + n).state_dict(), getattr(other, "net" + n).state_dict()
+        for k in want:                             # Adam's third step: needs the restored moments and step count
+            assert torch.allclose(got[k], want[k], rtol=0, atol=2e-5), (n, k)
+    assert int(other.optimizer_R.state[next(other.netR.parameters())]["step"]) == 3
+
+
+def test_loadable_model_round_trip(tmp_path):
+    from dfmir_b200 import vxm
+    torch.manual_seed(3)
+    R = vxm.VxmDense((32, 48), [[8, 16], [16, 16, 8]], int_steps=5, bidir=True).cuda()
+    path = os.path.join(tmp_path, "vxm.pt")
+    R.save(path)
+    ck = torch.load(path)
+    assert set(ck.keys()) == {"config", "model_state"} and not any(k.endswith(".grid") for k in ck["model_state"])
+    assert ck["config"]["inshape"] == (32, 48) and ck["config"]["int_steps"] == 5 and ck["config"]["bidir"] is True
+    R2 = vxm.VxmDense.load(path, "cuda")
+    a, b = R.state_dict(), R2.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k             # incl. the rebuilt .grid buffers
+    x = torch.randn(1, 1, 32, 48, device="cuda"); y = torch.randn(1, 1, 32, 48, device="cuda")
+    for u, v in zip(R(x, y), R2(x, y)):
+        assert torch.equal(u, v)

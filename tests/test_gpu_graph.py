@@ -58,3 +58,55 @@ def test_capture_needs_capturable_optimizers():
     model, _ = make(False)
     with pytest.raises(_lib.DfmirError):
         model.capture_step()
+
+
+def test_replays_draw_fresh_patch_ids_and_follow_the_lr_schedule():
+    """Every replay of the captured step draws new PatchSampleF positions (the Philox offset of the generator is a
+    graph input), and update_learning_rate() keeps the graph: capturable Adam reads the rate from a device tensor that
+    the scheduler fills in place (the reference's train.py steps the schedulers once per epoch)."""
+    model, data = make(True)
+    for _ in range(2):
+        model.optimize_parameters()
+    model.capture_step()
+    model.optimize_parameters()
+    ids1 = [t.clone() for t in model._last_patch_ids]
+    model.optimize_parameters()
+    ids2 = [t.clone() for t in model._last_patch_ids]
+    assert all(a.shape == b.shape for a, b in zip(ids1, ids2))
+    assert any(not torch.equal(a, b) for a, b in zip(ids1, ids2)), "two replays drew the same patch ids"
+    lr = model.optimizers[0].param_groups[0]['lr']
+    assert torch.is_tensor(lr) and lr.is_cuda
+    model.opt.n_epochs, model.opt.n_epochs_decay = 0, 3          # linear decay from the first epoch on
+    model.schedulers = [__import__('dfmir_b200').networks.get_scheduler(o, model.opt) for o in model.optimizers]
+    graph = model._graph
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.update_learning_rate()
+    assert model._graph is graph, "the captured step must survive a learning-rate update"
+    new_lr = float(model.optimizers[0].param_groups[0]['lr'])
+    assert 0 < new_lr < 2e-4
+    # Adam's first-moment direction is unchanged by the rate, so the parameter update scales with it
+    p = next(model.netR.parameters())
+    before = p.detach().clone()
+    model.optimize_parameters()
+    step_small = float((p.detach() - before).abs().max())
+    assert 0 < step_small <= new_lr * 1.5, (step_small, new_lr)
+
+
+def test_no_grad_forward_after_replay_uses_current_weights():
+    """Kernel-layout weight copies are cached by parameter version; graph replays update the parameters without bumping
+    it, so optimize_parameters() drops the caches after every replay: a no-grad forward (model.test())
+    between replays must see the current weights."""
+    from dfmir_b200 import functional as Fn, umma
+    model, data = make(True)
+    for _ in range(2):
+        model.optimize_parameters()
+    model.capture_step()
+    model.optimize_parameters()
+    model.test()                                   # caches kernel-layout copies under no_grad
+    for _ in range(3):
+        model.optimize_parameters()
+    model.test()
+    got = model.fake_B.clone()
+    Fn._pack_cache.clear(); umma._kmajor_cache.clear()
+    model.test()
+    assert torch.equal(got, model.fake_B), "a no-grad forward after graph replays ran on stale weight copies"

@@ -309,3 +309,139 @@ def test_patchnce_tensor_core_3xtf32(orc):
     np.testing.assert_allclose(res["auto"][1], res["simt"][1], atol=1e-4 * np.abs(res["simt"][1]).max())
     # the split products really ran on the tensor cores: a plain-TF32 product would be ~1e-2 off at T = 0.07
     assert np.abs(res["auto"][0] - res["simt"][0]).max() < 1e-4
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,pad", [(2, 256, 256, 66, 66, 0), (1, 256, 64, 20, 28, 1), (3, 512, 32, 18, 18, 0)])
+def test_dgrad_accumulates_into_prefilled_dx(N, Cin, Cout, H, W, pad):
+    """dfmir_conv_umma_dgrad_acc (CTA-pair kernel, accumulating epilogue): dx += conv_transpose(dy, w) on a dx that
+    already holds the skip connection's gradient (ResnetBlock, models/networks.py:1218-1221).  Against the float64
+    data gradient of TF32-truncated operands plus the pre-filled values, 3e-5 of the scale."""
+    from oracle import torch_port as tp
+    import dfmir_b200.functional as Fn
+    from dfmir_b200 import _lib
+    r = gi.rng(1200 + Cin + Cout + H)
+    OH, OW = H + 2 * pad - 2, W + 2 * pad - 2
+    dy = torch.from_numpy(r.standard_normal((N, Cout, OH, OW)).astype(np.float32))
+    w = torch.from_numpy((r.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cout * 9)).astype(np.float32))
+    pre = torch.from_numpy(r.standard_normal((N, Cin, H, W)).astype(np.float32))
+    want = pre.double() + torch.nn.grad.conv2d_input((N, Cin, H, W), tp.tf32_round(w).double(), tp.tf32_round(dy).double(), padding=pad)
+    dyg = dy.cuda().permute(0, 2, 3, 1).contiguous()
+    dx = pre.cuda().permute(0, 2, 3, 1).contiguous()
+    wk = w.cuda().reshape(Cout, Cin, 9).permute(2, 1, 0).contiguous()          # [tap][Cin][Cout]: K-major for the data gradient
+    d = Fn._make_desc(2, N, Cin, Cout, [H, W], [OH, OW], [3, 3], [pad, pad], 1, 0, Fn._cl_strides(dx, 2), Fn._cl_strides(dyg, 2))
+    assert _lib.lib().dfmir_conv_umma_dgrad_acc_supported(ctypes.byref(d))
+    _lib.call("dfmir_conv_umma_dgrad_acc", dyg, wk, dx, ctypes.byref(d))
+    got = dx.permute(0, 3, 1, 2).cpu().double()
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 3e-5 * scale
+    # the epilogue added to dx rather than overwriting it
+    assert float((got - pre.double()).abs().max()) > 1e-2
+
+
+def test_resnet_block_slot_handovers():
+    """The mutable side channels between the autograd nodes of a ResnetBlock (functional.BiasGradSlot,
+    ResidualGradSlot; networks.ResnetBlock.forward_padded): conv bias gradients summed by the InstanceNorm backward,
+    skip-connection gradient parked by the last norm's backward and completed by the first convolution's
+    accumulating data-gradient epilogue.  Two chained blocks at 256 channels against the float64 autograd of the
+    reference's module graph with TF32-truncated convolution operands (oracle/torch_port.py): every gradient at
+    accumulation-noise level, and the slot path equal to the slot-free path."""
+    from oracle import torch_port as tp
+    import dfmir_b200.functional as Fn
+    from dfmir_b200 import networks
+    import torch.nn as nn
+    import functools
+    r = gi.rng(1300)
+    N, C, Hh = 2, 256, 24
+    norm = functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False)
+    blocks = [networks.ResnetBlock(C, 'reflect', norm, False, True) for _ in range(2)]
+    for b in blocks:
+        for conv in (b.conv_block[1], b.conv_block[5]):
+            conv.weight.data = torch.from_numpy((r.standard_normal((C, C, 3, 3)) / np.sqrt(C * 9)).astype(np.float32))
+            conv.bias.data = torch.from_numpy(r.standard_normal(C).astype(np.float32) * 0.1)
+    x = torch.from_numpy(r.standard_normal((N, C, Hh, Hh)).astype(np.float32))
+    gy = torch.from_numpy(r.standard_normal((N, C, Hh, Hh)).astype(np.float32))
+
+    # float64 reference with truncated operands
+    tp.TF32_EMULATION = "trunc"
+    try:
+        xr = x.double().requires_grad_()
+        leaves = []
+        a = xr
+        for b in blocks:
+            w1, b1 = b.conv_block[1].weight.detach().double().requires_grad_(), b.conv_block[1].bias.detach().double().requires_grad_()
+            w2, b2 = b.conv_block[5].weight.detach().double().requires_grad_(), b.conv_block[5].bias.detach().double().requires_grad_()
+            leaves += [w1, b1, w2, b2]
+            h = F.relu(F.instance_norm(tp.conv2d(F.pad(a, (1,) * 4, mode='reflect'), w1, b1)))
+            h = F.instance_norm(tp.conv2d(F.pad(h, (1,) * 4, mode='reflect'), w2, b2))
+            a = a + h
+        (a * gy.double()).sum().backward()
+    finally:
+        tp.TF32_EMULATION = None
+
+    def run(use_slots):
+        for b in blocks:
+            b.cuda()
+            b.zero_grad()
+        xg = x.cuda().permute(0, 2, 3, 1).contiguous().requires_grad_()
+        P = Fn.pad_reflect_cl(xg, 1)
+        for i, b in enumerate(blocks):
+            op = 1 if i == 0 else 0
+            if use_slots:
+                P = b.forward_padded(P, op)
+            else:
+                c1, c2 = b.conv_block[1], b.conv_block[5]
+                y = Fn.conv_cl(P, c1.weight, c1.bias)
+                P1 = Fn.instnorm_cl(y, relu=True, out_pad=1)
+                y = Fn.conv_cl(P1, c2.weight, c2.bias)
+                P = Fn.instnorm_cl(y, relu=False, out_pad=op, res=P, res_pad=1)
+        (P * gy.cuda().permute(0, 2, 3, 1)).sum().backward()
+        params = [p.grad.detach().cpu().double() for b in blocks for p in (b.conv_block[1].weight, b.conv_block[1].bias,
+                                                                         b.conv_block[5].weight, b.conv_block[5].bias)]
+        return P.detach().permute(0, 3, 1, 2).cpu().double(), xg.grad.permute(0, 3, 1, 2).cpu().double(), params
+
+    prev_engine, prev_min = Fn.CONV_ENGINE, Fn.UMMA_MIN_POSITIONS
+    Fn.CONV_ENGINE, Fn.UMMA_MIN_POSITIONS = "auto", 0
+    try:
+        out_s, dx_s, gr_s = run(True)
+        out_n, dx_n, gr_n = run(False)
+    finally:
+        Fn.CONV_ENGINE, Fn.UMMA_MIN_POSITIONS = prev_engine, prev_min
+    assert float((out_s - a.detach()).abs().max()) <= 3e-5 * float(a.detach().abs().max())
+    wscale = max(float(l.grad.abs().max()) for l in leaves[0::2])
+    for name, got_s, got_n, want in [("dx", dx_s, dx_n, xr.grad)] + [(f"param{i}", gs, gn, l.grad) for i, (gs, gn, l) in enumerate(zip(gr_s, gr_n, leaves))]:
+        sc = float(want.abs().max())
+        if name.startswith("param") and int(name[5:]) % 2 == 1:
+            sc = wscale       # conv biases in front of an instance norm: the true gradient is zero, compare on the weights' scale
+        assert float((got_s - want).abs().max()) <= 1e-4 * sc, (name, "slots vs truncated float64", float((got_s - want).abs().max()), sc)
+        assert float((got_s - got_n).abs().max()) <= 3e-5 * sc, (name, "slot path vs slot-free path")
+
+
+def test_sparse_tap_gradient_equals_dense():
+    """PatchNCE taps (functional.gather_patches): the sparse COO gradient of a tapped activation that autograd
+    index-adds into the dense gradient arriving from the next layer must equal the dense scatter path."""
+    import dfmir_b200.functional as Fn
+    r = gi.rng(1400)
+    B, H, W, C, P = 3, 20, 24, 32, 64
+    x = torch.from_numpy(r.standard_normal((B, H, W, C)).astype(np.float32)).cuda()
+    ids = torch.from_numpy(r.permutation(H * W)[:P]).cuda()
+    gw = torch.from_numpy(r.standard_normal((B * P, C)).astype(np.float32)).cuda()
+    gd = torch.from_numpy(r.standard_normal((B, H, W, C)).astype(np.float32)).cuda()
+    res = {}
+    for sparse in (True, False):
+        prev = Fn.SPARSE_TAP_GRAD
+        Fn.SPARSE_TAP_GRAD = sparse
+        try:
+            xl = x.clone().requires_grad_()
+            y = xl * 1.0                               # a non-leaf channels-last activation, as in ResnetGenerator.forward
+            v = y.permute(0, 3, 1, 2)
+            v._dfmir_cl = y
+            rows = Fn.gather_patches(v, ids)
+            ((rows * gw).sum() + (y * gd).sum()).backward()      # tap gradient + the next layer's dense gradient
+            res[sparse] = (rows.detach().clone(), xl.grad.clone())
+        finally:
+            Fn.SPARSE_TAP_GRAD = prev
+    assert torch.equal(res[True][0], res[False][0])
+    want = gd.clone().view(B, H * W, C)
+    want[:, ids, :] += gw.view(B, P, C)
+    assert torch.equal(res[False][1], want.view(B, H, W, C))
+    assert torch.allclose(res[True][1], res[False][1], rtol=0, atol=1e-6)

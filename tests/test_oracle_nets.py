@@ -108,3 +108,62 @@ def test_torch_port_step(golden, monkeypatch):
                 if not exact_zero:   # Adam turns a noise gradient into a +-lr step: nothing to compare there
                     sel = np.abs(want) > 1e-3 * np.abs(want).max()
                     np.testing.assert_allclose(p.detach().numpy()[sel], g[f"sd1/{n}/{k}"][sel], atol=2e-5, err_msg=f"{n}.{k}")
+
+
+@pytest.mark.parametrize("name,shape,seed", [("n2d", (64, 64), 71), ("n3d", (24, 28, 32), 72), ("n2d_odd", (45, 70), 73)])
+def test_torch_port_ncc_loss(name, shape, seed, golden):
+    """oracle/torch_port.ncc_loss (the CPU-baseline composition of bench.py's 3-D legs) against the reference's own
+    NCC_Loss values and gradients (tests/golden/losses.npz, generated by oracle/gen_golden.py)."""
+    import torch
+    from oracle import torch_port as tp
+    g = golden("losses")
+    I = torch.from_numpy(gi.image_textured(seed, 2, shape)).requires_grad_()
+    J = torch.from_numpy(gi.image_textured(seed + 1, 2, shape)).requires_grad_()
+    loss = tp.ncc_loss(I, J, 9)
+    loss.backward()
+    assert abs(float(loss) - float(g[name + "/loss"])) <= 1e-6
+    np.testing.assert_allclose(I.grad.numpy(), g[name + "/dI"], atol=1e-6 * max(1.0, np.abs(g[name + "/dI"]).max()), rtol=1e-4)
+    np.testing.assert_allclose(J.grad.numpy(), g[name + "/dJ"], atol=1e-6 * max(1.0, np.abs(g[name + "/dJ"]).max()), rtol=1e-4)
+    mask = torch.from_numpy((gi.image(seed + 2, 2, shape) > -0.5).astype(np.float32))
+    assert abs(float(tp.ncc_loss(I.detach(), J.detach(), 9, mask=mask)) - float(g[name + "/loss_masked"])) <= 1e-6
+
+
+def test_torch_port_grad_loss(golden):
+    import torch
+    from oracle import torch_port as tp
+    g = golden("losses")
+    assert abs(float(tp.grad_loss(torch.from_numpy(g["survey/grad_in"]))) - float(g["survey/grad_l2_3d"])) <= 1e-6
+    for name, shape, seed in [("g2d", (64, 80), 81), ("g3d", (12, 16, 20), 82)]:
+        x = torch.from_numpy(gi.weights(seed, (2, len(shape), *shape), 1.0)).requires_grad_()
+        for pen in ("l1", "l2"):
+            x.grad = None
+            loss = tp.grad_loss(x, pen) * (2.0 if pen == "l1" else 1.0)     # the l1 goldens carry loss_mult = 2
+            loss.backward()
+            assert abs(float(loss) - float(g[f"{name}/{pen}"])) <= 1e-6 * max(1.0, abs(float(g[f"{name}/{pen}"])))
+            np.testing.assert_allclose(x.grad.numpy(), g[f"{name}/{pen}_dx"], atol=1e-9, rtol=1e-5)
+
+
+def test_torch_port_step3d_matches_reference_vxm(golden):
+    """Step3D.forward (the 3-D CPU baseline of bench.py) against the reference's own VxmDense-3D forward / backward
+    with default features at 16 x 32 x 16 (tests/golden/nets3d.npz, oracle/gen_golden.py gen_nets3d)."""
+    import torch
+    from oracle import torch_port as tp
+    g = golden("nets3d")
+    sd = {k[len("R3d/sd/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("R3d/sd/")}
+    shape = (16, 32, 16)
+    st = tp.Step3D(sd, [[16, 32, 32, 32], [32, 32, 32, 32, 32, 16, 16]])
+    src = torch.from_numpy(gi.image_textured(241, 1, shape)).requires_grad_()
+    tgt = torch.from_numpy(gi.image_textured(242, 1, shape))
+    ys, flow = st.forward(src, tgt)
+    np.testing.assert_allclose(ys.detach().numpy(), g["R3d/y_source"], atol=2e-6)
+    np.testing.assert_allclose(flow.detach().numpy(), g["R3d/pos_flow"], atol=2e-6)
+    loss = (ys * torch.from_numpy(gi.weights(243, tuple(ys.shape), 1.0))).sum() + (flow * torch.from_numpy(gi.weights(245, tuple(flow.shape), 0.1))).sum()
+    loss.backward()
+    np.testing.assert_allclose(src.grad.numpy(), g["R3d/d_src"], atol=1e-5 * np.abs(g["R3d/d_src"]).max())
+    for k, v in st.P.items():
+        if v.grad is not None:
+            want = g["R3d/grad/" + k]
+            np.testing.assert_allclose(v.grad.numpy(), want, atol=1e-4 * max(1e-6, np.abs(want).max()), err_msg=k)
+    # and one optimiser step of the composition bench.py times runs
+    st.step(src.detach(), tgt)
+    assert np.isfinite(st.losses['ncc']) and np.isfinite(st.losses['grad'])
