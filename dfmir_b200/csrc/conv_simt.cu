@@ -420,10 +420,11 @@ int fill_geom(ConvP& p, const dfmir_conv_desc* d, const char* who) {
     if (d->in_shape[a] < 1 || d->out_shape[a] < 1 || d->kernel[a] < 1 || d->pad[a] < 0) {
       dfmir_set_error("%s: bad spatial geometry on axis %d", who, a); return DFMIR_ERR_ARG;
     }
-    // forward output size of a (strided, zero-padded) convolution
+    // forward output size of a (strided, zero-padded) convolution; a smaller out_shape is the same convolution with less
+    // trailing padding (pad = leading padding: the space-to-depth form of a stride-2 layer pads one side only)
     const int want = (d->in_shape[a] + 2 * d->pad[a] - d->kernel[a]) / d->stride + 1;
-    if (want != d->out_shape[a]) {
-      dfmir_set_error("%s: out_shape[%d]=%d inconsistent with in=%d k=%d pad=%d stride=%d (expected %d)", who, a,
+    if (d->out_shape[a] > want) {
+      dfmir_set_error("%s: out_shape[%d]=%d inconsistent with in=%d k=%d pad=%d stride=%d (expected at most %d)", who, a,
                       d->out_shape[a], d->in_shape[a], d->kernel[a], d->pad[a], d->stride, want);
       return DFMIR_ERR_ARG;
     }

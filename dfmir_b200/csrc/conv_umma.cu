@@ -54,7 +54,34 @@ struct UmmaP {
   int per_sample;         // 1: the "tap" coordinate of the weight map is the sample index (batched A[b] * B[b]^T)
   int accum;              // 1: y += result (CTA-pair kernel only: the residual branch's gradient is already in y)
   long long ys[5];        // output element strides n, d, h, w, c
+  float2* stat_rows;      // nullable: per-(32-voxel row group, channel) {sum, sum of squares} of the stored result, the
+                          // InstanceNorm statistics of the layer that follows (halo / CTA-pair kernels), [row][Cout]
 };
+
+// Column sums of a 32 x 32 register tile held one row per lane: after five exchange steps lane L holds the sum over
+// the 32 lanes of element L (31 shuffles instead of 160 for 32 separate warp reductions).  v is destroyed.
+template <int K>
+__device__ __forceinline__ void col_sum_step(float* v, int lane) {
+  const bool up = (lane & K) != 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float send = up ? v[j] : v[j + K];
+    const float keep = up ? v[j + K] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, K);
+  }
+}
+__device__ __forceinline__ float col_sum32(float* v, int lane) {
+  col_sum_step<16>(v, lane); col_sum_step<8>(v, lane); col_sum_step<4>(v, lane); col_sum_step<2>(v, lane); col_sum_step<1>(v, lane);
+  return v[0];
+}
+// InstanceNorm statistics by-product of an epilogue: v = this lane's 32 stored channel values (garbage if !valid)
+__device__ __forceinline__ void emit_stat_row(float* v, bool valid, int lane, float2* row, int c_first, int Cout) {
+  float sq[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+  const float s1 = col_sum32(v, lane), s2 = col_sum32(sq, lane);
+  if (c_first + lane < Cout) row[c_first + lane] = make_float2(s1, s2);
+}
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == DFMIR_ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
@@ -470,6 +497,10 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (n0 + c0 + i < p.Cout) yp[(long long)(n0 + c0 + i) * p.ys[4]] = v[i];
             }
           }
+          if constexpr (CW == 32) {
+            if (p.stat_rows)         // uniform per launch; every lane takes part in the exchange
+              emit_stat_row(v, valid, lane, p.stat_rows + ((long long)(pt * MT + j) * 4 + quarter) * p.Cout, n0 + c0, p.Cout);
+          }
         }
       }
       tc_fence_before();
@@ -696,6 +727,8 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               }
           }
         }
+        if (p.stat_rows && n < p.N)
+          emit_stat_row(v, valid, lane, p.stat_rows + ((long long)pt * 4 + quarter) * p.Cout, n0 + c0, p.Cout);
       }
       tc_fence_before();
       __syncwarp();
@@ -709,6 +742,10 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // ---------------------------------------------------------------- host side
+// InstanceNorm-statistics by-product of a forward launch (dfmir_conv_umma_fwd_stats): `query` only reports how many
+// statistic rows per image the kernel variant chosen for this shape writes (0: that variant has no such epilogue)
+struct StatArg { float2* buf; bool query; int rows_per_image; };
+
 // strides arrive as {n, spatial[nd], c}
 struct Strides5 { long long n, d, h, w, c; };
 Strides5 spread(const long long* s, int nd) {
@@ -756,7 +793,7 @@ int fill_umma(UmmaP& p, const dfmir_conv_desc* d, int dgrad, const char* who) {
   }
   p.KD = K[0]; p.KH = K[1]; p.KW = K[2]; p.pad_d = P[0]; p.pad_h = P[1]; p.pad_w = P[2];
   p.D = O[0]; p.H = O[1]; p.W = O[2];
-  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act; p.per_sample = 0; p.accum = 0;
+  p.flip = dgrad; p.act = dgrad ? DFMIR_ACT_NONE : d->act; p.per_sample = 0; p.accum = 0; p.stat_rows = nullptr;
   const Strides5 os = spread(dgrad ? d->x_strides : d->y_strides, nd);
   p.ys[0] = os.n; p.ys[1] = os.d; p.ys[2] = os.h; p.ys[3] = os.w; p.ys[4] = os.c;
   // tile box TD x TH x TW = 128 voxels (powers of two, TW >= 8): the shape that wastes the fewest voxels on
@@ -797,7 +834,7 @@ int launch_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const float* bia
 
 template <int BN, int SD, int SH, int SW, int BST, int KDT>
 int launch_halo_k(const float* act, const Strides5& as, int ID, int IH, int IW, const CUtensorMap& tmB, const float* bias, float* y,
-                UmmaP p, cudaStream_t st, const char* who) {
+                UmmaP p, cudaStream_t st, const char* who, StatArg* stat) {
   using C = HaloCfg<BN, SD, SH, SW, BST>;
   HaloP hp;
   hp.HD = SD + p.KD - 1; hp.HH = 16 * SH + p.KH - 1; hp.HW = 8 * SW + p.KW - 1;
@@ -807,6 +844,12 @@ int launch_halo_k(const float* act, const Strides5& as, int ID, int IH, int IW, 
   if (smem > 227 * 1024 || hp.HW > 256 || hp.HH > 256 || hp.HD > 256) return DFMIR_ERR_UNSUPPORTED;
   p.tiles_d = (p.D + SD - 1) / SD; p.tiles_h = (p.H + 16 * SH - 1) / (16 * SH); p.tiles_w = (p.W + 8 * SW - 1) / (8 * SW);
   p.ptiles = p.N * p.tiles_d * p.tiles_h * p.tiles_w;
+  if (stat) {
+    stat->rows_per_image = BN >= 32 ? p.tiles_d * p.tiles_h * p.tiles_w * C::MT * 4 : 0;
+    if (stat->query) return DFMIR_OK;
+    if (stat->buf && stat->rows_per_image == 0) { dfmir_set_error("%s: no statistics epilogue for 16-channel tiles", who); return DFMIR_ERR_UNSUPPORTED; }
+    p.stat_rows = stat->buf;
+  }
   hp.u = p;
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   CUtensorMap tmA;
@@ -833,19 +876,19 @@ int launch_halo_k(const float* act, const Strides5& as, int ID, int IH, int IW, 
 // 3 x 3 (x 3) kernels take the instantiation with compile-time taps; 2-D tile configurations have SD = 1
 template <int BN, int SD, int SH, int SW, int BST>
 int launch_halo(const float* act, const Strides5& as, int ID, int IH, int IW, const CUtensorMap& tmB, const float* bias, float* y,
-                UmmaP p, cudaStream_t st, const char* who) {
+                UmmaP p, cudaStream_t st, const char* who, StatArg* stat) {
   static const int fixed = getenv("DFMIR_UMMA_FIXED_TAPS") ? atoi(getenv("DFMIR_UMMA_FIXED_TAPS")) : 1;
   constexpr int KDT = SD > 1 ? 3 : 1;
   if (fixed && p.KH == 3 && p.KW == 3 && p.KD == KDT)
-    return launch_halo_k<BN, SD, SH, SW, BST, KDT>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-  return launch_halo_k<BN, SD, SH, SW, BST, 0>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+    return launch_halo_k<BN, SD, SH, SW, BST, KDT>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
+  return launch_halo_k<BN, SD, SH, SW, BST, 0>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
 }
 
 // CTA-pair kernel: 2-D 3 x 3 convolutions with Cout a multiple of BN = 256 or 128 (ResnetBlock and down / up-sampling
 // convs of the generator, forward and data gradient)
 template <int BN>
 int launch_pair(const float* act, const Strides5& as, int IH, int IW, const float* w, const float* bias, float* y, UmmaP p,
-                cudaStream_t st, const char* who) {
+                cudaStream_t st, const char* who, StatArg* stat) {
   HaloP hp;
   hp.HD = 1; hp.HH = 18; hp.HW = 10;
   hp.a_bytes = (hp.HH * hp.HW * 128 + 1023) / 1024 * 1024;
@@ -854,6 +897,11 @@ int launch_pair(const float* act, const Strides5& as, int IH, int IW, const floa
   const size_t smem = 2 * (size_t)hp.a_bytes + (size_t)PAIR_BST * PAIR_B_BYTES + nbars * 8 + 16 + 1024;
   p.tiles_d = 1; p.tiles_h = (p.H + 15) / 16; p.tiles_w = (p.W + 7) / 8;
   p.ptiles = p.N * p.tiles_h * p.tiles_w;
+  if (stat) {
+    stat->rows_per_image = p.tiles_h * p.tiles_w * 4;
+    if (stat->query) return DFMIR_OK;
+    p.stat_rows = stat->buf;
+  }
   hp.u = p;
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   CUtensorMap tmA, tmB;
@@ -889,7 +937,7 @@ int launch_pair(const float* act, const Strides5& as, int IH, int IW, const floa
 
 // act: source activation (channels-last, c stride 1) with element strides `as` and spatial size (ID, IH, IW)
 int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const float* w, const float* bias, float* y,
-             const UmmaP& p, cudaStream_t st, const char* who) {
+             const UmmaP& p, cudaStream_t st, const char* who, StatArg* stat = nullptr) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   if (!enc) { dfmir_set_error("%s: cuTensorMapEncodeTiled not available from the driver", who); return DFMIR_ERR_CUDA; }
   if (((uintptr_t)act & 15) || ((uintptr_t)w & 15)) { dfmir_set_error("%s: TMA needs 16-byte aligned base pointers", who); return DFMIR_ERR_ARG; }
@@ -906,9 +954,9 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
     return DFMIR_ERR_UNSUPPORTED;
   }
   if (pair && ID == 1 && p.KD == 1 && p.KH == 3 && p.KW == 3 && p.Cin % KCH == 0 && !p.per_sample && p.ys[4] == 1) {
-    if (p.Cout % 256 == 0) return launch_pair<256>(act, as, IH, IW, w, bias, y, p, st, who);
+    if (p.Cout % 256 == 0) return launch_pair<256>(act, as, IH, IW, w, bias, y, p, st, who, stat);
     // DFMIR_UMMA_PAIR=2 also pairs the 128-channel layers: measured slower than the single-CTA 2 x 128 tiles (5.7 vs 5.2 ms / step)
-    if (p.Cout % 128 == 0 && pair > 1) return launch_pair<128>(act, as, IH, IW, w, bias, y, p, st, who);
+    if (p.Cout % 128 == 0 && pair > 1) return launch_pair<128>(act, as, IH, IW, w, bias, y, p, st, who, stat);
   }
   CUtensorMap tmA, tmB;
   {
@@ -934,23 +982,28 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
   // halo variant (one activation tile per chunk serves every tap): kernels larger than 1x1
   static const int halo = getenv("DFMIR_UMMA_HALO") ? atoi(getenv("DFMIR_UMMA_HALO")) : 1;
   if (halo && narrow256) {
-    int rc = launch_halo<256, 1, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+    int rc = launch_halo<256, 1, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
     if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
   }
   if (halo && p.KD * p.KH * p.KW > 1 && BN <= 128) {
     int rc = DFMIR_ERR_UNSUPPORTED;
     if (ID > 1) {
-      if (BN == 128) rc = launch_halo<128, 2, 1, 1, 2>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-      else if (BN == 64) rc = launch_halo<64, 2, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-      else if (BN == 32) rc = launch_halo<32, 2, 1, 1, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-      else rc = launch_halo<16, 2, 1, 1, 8>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      if (BN == 128) rc = launch_halo<128, 2, 1, 1, 2>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
+      else if (BN == 64) rc = launch_halo<64, 2, 1, 1, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
+      else if (BN == 32) rc = launch_halo<32, 2, 1, 1, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
+      else rc = launch_halo<16, 2, 1, 1, 8>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
     } else {
-      if (BN == 128) rc = launch_halo<128, 1, 1, 2, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-      else if (BN == 64) rc = launch_halo<64, 1, 2, 2, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-      else if (BN == 32) rc = launch_halo<32, 1, 2, 2, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
-      else rc = launch_halo<16, 1, 2, 2, 8>(act, as, ID, IH, IW, tmB, bias, y, p, st, who);
+      if (BN == 128) rc = launch_halo<128, 1, 1, 2, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
+      else if (BN == 64) rc = launch_halo<64, 1, 2, 2, 4>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
+      else if (BN == 32) rc = launch_halo<32, 1, 2, 2, 6>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
+      else rc = launch_halo<16, 1, 2, 2, 8>(act, as, ID, IH, IW, tmB, bias, y, p, st, who, stat);
     }
     if (rc != DFMIR_ERR_UNSUPPORTED) return rc;
+  }
+  if (stat) {         // the plain variant has no statistics epilogue
+    stat->rows_per_image = 0;
+    if (stat->query) return DFMIR_OK;
+    if (stat->buf) { dfmir_set_error("%s: no statistics epilogue for this shape", who); return DFMIR_ERR_UNSUPPORTED; }
   }
   // plain variant (1x1 kernels, DFMIR_UMMA_HALO=0).  128-channel tiles x 2 sub-tiles: 48 KB stages x 4 and
   // double-buffered accumulators beat one 256-wide tile (64 KB x 3, no epilogue overlap): 552 vs 430 TFLOP/s on the
@@ -976,6 +1029,36 @@ extern "C" int dfmir_conv_umma_fwd(const float* x, const float* w, const float* 
   const int nd = d->nd;
   return run_umma(x, spread(d->x_strides, nd), nd == 3 ? d->in_shape[0] : 1, d->in_shape[nd - 2], d->in_shape[nd - 1], w, bias, y, p,
                   (cudaStream_t)stream, "dfmir_conv_umma_fwd");
+}
+
+// Forward + the InstanceNorm statistics of its result as a by-product of the epilogue (models/networks.py:984,996,1020,
+// 1201-1215: every generator convolution is followed by InstanceNorm2d): while a 32-voxel x 32-channel block of the result
+// is in registers, its per-channel sum and sum of squares go to stat_rows[(image-major row)][Cout] as float2, which
+// dfmir_instnorm_fwd_rows reduces instead of a pass over y.  dfmir_conv_umma_stat_rows: rows per image the kernel
+// chosen for this shape writes, 0 if it has no such epilogue (then call dfmir_conv_umma_fwd and dfmir_instnorm_fwd).
+extern "C" int dfmir_conv_umma_stat_rows(const dfmir_conv_desc* d) {
+  UmmaP p;
+  if (!umma_shape_ok(d, 0) || fill_umma(p, d, 0, "dfmir_conv_umma_stat_rows")) return 0;
+  const int nd = d->nd;
+  if (d->y_strides[nd + 1] != 1 || d->Cout % 4) return 0;
+  StatArg stat{nullptr, true, 0};
+  // 16-byte aligned dummy pointers: only the tile geometry is evaluated
+  if (run_umma((const float*)16, spread(d->x_strides, nd), nd == 3 ? d->in_shape[0] : 1, d->in_shape[nd - 2], d->in_shape[nd - 1],
+               (const float*)16, nullptr, (float*)16, p, nullptr, "dfmir_conv_umma_stat_rows", &stat)) return 0;
+  return stat.rows_per_image;
+}
+
+extern "C" int dfmir_conv_umma_fwd_stats(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
+                                         float* stat_rows, void* stream) {
+  UmmaP p;
+  int rc = fill_umma(p, d, 0, "dfmir_conv_umma_fwd_stats");
+  if (rc) return rc;
+  DFMIR_CHECK_ARG(x && w && y && stat_rows, "dfmir_conv_umma_fwd_stats: null pointer");
+  DFMIR_CHECK_ARG(((uintptr_t)stat_rows & 7) == 0, "dfmir_conv_umma_fwd_stats: stat_rows must be 8-byte aligned");
+  const int nd = d->nd;
+  StatArg stat{(float2*)stat_rows, false, 0};
+  return run_umma(x, spread(d->x_strides, nd), nd == 3 ? d->in_shape[0] : 1, d->in_shape[nd - 2], d->in_shape[nd - 1], w, bias, y, p,
+                  (cudaStream_t)stream, "dfmir_conv_umma_fwd_stats", &stat);
 }
 
 // Data gradient on the tensor cores: dx = conv(dy, flipped taps, pad' = k-1-pad).
@@ -1024,7 +1107,7 @@ extern "C" int dfmir_bmm_nt_umma(const float* A, const float* B, float* C, int b
   p.N = batch; p.D = 1; p.H = 1; p.W = M; p.Cin = K; p.Cout = N;
   p.KD = p.KH = p.KW = 1; p.pad_d = p.pad_h = p.pad_w = 0;
   p.TD = 1; p.TH = 1; p.TW = 128; p.tiles_d = 1; p.tiles_h = 1; p.tiles_w = M / 128;
-  p.ptiles = batch * p.tiles_w; p.flip = 0; p.act = DFMIR_ACT_NONE; p.per_sample = 1; p.accum = 0;
+  p.ptiles = batch * p.tiles_w; p.flip = 0; p.act = DFMIR_ACT_NONE; p.per_sample = 1; p.accum = 0; p.stat_rows = nullptr;
   p.ys[0] = (long long)M * N; p.ys[1] = 0; p.ys[2] = 0; p.ys[3] = N; p.ys[4] = 1;
   const int mt = N <= 64 ? 4 : 2;      // sub-tiles per work item of the tile configuration run_umma picks
   DFMIR_CHECK_ARG(p.tiles_w % mt == 0, "%s: M = %d must be a multiple of %d so that a work item stays inside one sample", who, M, 128 * mt);

@@ -70,6 +70,35 @@ __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __res
   stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Statistics from the per-row-group sums a convolution epilogue wrote (dfmir_conv_umma_fwd_stats):
+// rows [n][rows_per_image][C] of {sum, sum of squares} over <= 32 voxels each -> stats (mean, rstd), summed in fp64 in a
+// fixed order.  grid (C / 32, N); thread = (channel of the 32-channel group, one of 8 row lanes).
+__global__ void __launch_bounds__(256)
+in_finalize_rows_kernel(const float2* __restrict__ rows, float* __restrict__ stats, int rows_per_image, int C, int HW, float eps) {
+  __shared__ double red[8][32][2];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl, n = blockIdx.y;
+  double s = 0, ss = 0;
+  if (c < C) {
+    const float2* rb = rows + (long long)n * rows_per_image * C + c;
+    for (int r = rl; r < rows_per_image; r += 8) {
+      const float2 v = rb[(long long)r * C];
+      s += (double)v.x; ss += (double)v.y;
+    }
+  }
+  red[rl][cl][0] = s; red[rl][cl][1] = ss;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int l = 1; l < 8; ++l) { s += red[l][cl][0]; ss += red[l][cl][1]; }
+    const double m = s / HW;
+    double var = ss / HW - m * m;
+    if (var < 0) var = 0;
+    stats[((long long)n * C + c) * 2] = (float)m;
+    stats[((long long)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 // y[n, hp, wp, c] = act((x[n,h,w,c] - mean) * rstd) (+ res[n, h+rp, w+rp, c]); (h,w) = reflect(hp-p, wp-p)
 __global__ void __launch_bounds__(256)
 in_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ res,
@@ -649,7 +678,49 @@ upcat_bwd_kernel(const float* __restrict__ dy, float* __restrict__ da, float* __
   }
 }
 
+// ------------------------------------------------------------------ space-to-depth (stride-2 convolutions on the tensor cores)
+// y[n, jd, jh, jw, ((pd*2 + ph)*2 + pw)*C + c] = x[n, 2jd+pd, 2jh+ph, 2jw+pw, c]   (2-D: no d axis, 4C channels)
+// A stride-2 3^nd convolution with pad 1 over x (vxm networks.py:1514-1515, the U-Net encoder) is a stride-1 2^nd
+// convolution over y with one leading zero row per axis, which the tcgen05 implicit-GEMM kernels run as they are.
+// V = elements per access (the channel count is a multiple of V).  inverse = the adjoint / inverse permutation.
+template <typename T>
+__global__ void __launch_bounds__(256)
+s2d_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int OD, int OH, int OW, int CV, int nd3, int inverse) {
+  const int P = nd3 ? 8 : 4;
+  const long long total = (long long)N * OD * OH * OW * P * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int c = (int)(q % CV); q /= CV;
+    const int par = (int)(q % P); q /= P;
+    const int jw = (int)(q % OW); q /= OW;
+    const int jh = (int)(q % OH); q /= OH;
+    const int jd = (int)(q % OD); q /= OD;
+    const int n = (int)q;
+    const int pw = par & 1, ph = (par >> 1) & 1, pd = nd3 ? (par >> 2) : 0;
+    const int ID = nd3 ? 2 * OD : 1;
+    const long long full = ((((long long)n * ID + (nd3 ? 2 * jd + pd : 0)) * (2 * OH) + 2 * jh + ph) * (2 * OW) + 2 * jw + pw) * CV + c;
+    if (inverse) dst[full] = src[i]; else dst[i] = src[full];
+  }
+}
+
 }  // namespace
+
+extern "C" int dfmir_space_to_depth(const float* src, float* dst, int N, int nd, const int* out_shape, int C, int inverse, void* stream) {
+  DFMIR_CHECK_ARG(src && dst && N > 0 && C > 0 && (nd == 2 || nd == 3) && out_shape, "dfmir_space_to_depth: bad argument");
+  const int OD = nd == 3 ? out_shape[0] : 1, OH = out_shape[nd - 2], OW = out_shape[nd - 1];
+  DFMIR_CHECK_ARG(OD > 0 && OH > 0 && OW > 0, "dfmir_space_to_depth: bad shape");
+  const long long total = (long long)N * OD * OH * OW * (nd == 3 ? 8 : 4) * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uintptr_t al = (uintptr_t)src | (uintptr_t)dst;
+  if (C % 4 == 0 && (al & 15) == 0)
+    s2d_kernel<float4><<<ew_grid(total / 4), 256, 0, st>>>((const float4*)src, (float4*)dst, N, OD, OH, OW, C / 4, nd == 3, inverse);
+  else if (C % 2 == 0 && (al & 7) == 0)
+    s2d_kernel<float2><<<ew_grid(total / 2), 256, 0, st>>>((const float2*)src, (float2*)dst, N, OD, OH, OW, C / 2, nd == 3, inverse);
+  else
+    s2d_kernel<float><<<ew_grid(total), 256, 0, st>>>(src, dst, N, OD, OH, OW, C, nd == 3, inverse);
+  DFMIR_CHECK_LAUNCH("dfmir_space_to_depth");
+  return DFMIR_OK;
+}
 
 // [sums: 2*N*C doubles][per-CTA partials: chunks * 2*N*C doubles, chunks * N <= 16 * SMs + 2 * N]
 extern "C" size_t dfmir_instnorm_workspace_bytes(int N, int C) {
@@ -698,6 +769,30 @@ extern "C" int dfmir_instnorm_fwd(const float* x, const float* res, float* y, fl
     in_apply_kernel<<<ew_grid(total), 256, 0, st>>>(x, stats, res, y, N, H, W, C, relu, out_pad, res_pad);
   }
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd(apply)");
+  return DFMIR_OK;
+}
+
+// The same layer with the statistics taken from the producing convolution's epilogue (dfmir_conv_umma_fwd_stats)
+// instead of a pass over x: stat_rows [N][rows_per_image][C] float2.
+extern "C" int dfmir_instnorm_fwd_rows(const float* x, const float* res, float* y, float* stats, const float* stat_rows,
+                                       int rows_per_image, int N, int H, int W, int C, float eps, int relu, int out_pad,
+                                       int res_pad, void* stream) {
+  DFMIR_CHECK_ARG(x && y && stats && stat_rows && rows_per_image > 0, "dfmir_instnorm_fwd_rows: null pointer");
+  DFMIR_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0, "dfmir_instnorm_fwd_rows: bad sizes");
+  DFMIR_CHECK_ARG(out_pad >= 0 && out_pad < H && out_pad < W && res_pad >= 0, "dfmir_instnorm_fwd_rows: bad padding");
+  DFMIR_CHECK_ARG(N <= 65535, "dfmir_instnorm_fwd_rows: batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  in_finalize_rows_kernel<<<dim3((C + 31) / 32, N), 256, 0, st>>>((const float2*)stat_rows, stats, rows_per_image, C, H * W, eps);
+  DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd_rows(finalize)");
+  if (in_v4_ok(C, x, y, res, stats) && H + 2 * out_pad <= 65535) {
+    int ach; const int achunk = apply_chunk((H + 2 * out_pad) * (W + 2 * out_pad), N, &ach);
+    in_apply_v4_kernel<<<dim3(ach, N), 256, 0, st>>>((const float4*)x, (const float4*)stats, (const float4*)res, (float4*)y, H, W,
+                                                     C / 4, relu, out_pad, res_pad, achunk);
+  } else {
+    const long long total = (long long)N * (H + 2 * out_pad) * (W + 2 * out_pad) * C;
+    in_apply_kernel<<<ew_grid(total), 256, 0, st>>>(x, stats, res, y, N, H, W, C, relu, out_pad, res_pad);
+  }
+  DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd_rows(apply)");
   return DFMIR_OK;
 }
 

@@ -126,7 +126,8 @@ class _ConvFn(torch.autograd.Function):
     """y = act(conv(x, w) + b); x (N,*S,Cin) channels-last (any strides), w (taps,Cin,Cout)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, kernel, stride, pad, act, planar_out, bias_slot=None, res_slot=None):
+    def forward(ctx, x, w, bias, kernel, stride, pad, act, planar_out, bias_slot=None, res_slot=None, out_shape=None,
+                flop_scale=1.0, stats_slot=None):
         ctx.bias_slot = bias_slot if act == ACT_NONE else None
         ctx.res_slot = res_slot
         _lib.require_cuda(x, w)
@@ -137,7 +138,8 @@ class _ConvFn(torch.autograd.Function):
         Cout = w.shape[2]
         if w.shape[0] != math.prod(kernel) or w.shape[1] != Cin:
             raise _lib.DfmirError(f"conv: weight {tuple(w.shape)} does not match kernel {kernel} / Cin {Cin}")
-        O = [(S[i] + 2 * pad[i] - kernel[i]) // stride + 1 for i in range(nd)]
+        # out_shape: `pad` is the LEADING padding only (space-to-depth form of a strided layer, conv_cl)
+        O = list(out_shape) if out_shape is not None else [(S[i] + 2 * pad[i] - kernel[i]) // stride + 1 for i in range(nd)]
         if planar_out:
             y = torch.empty((N, Cout, *O), dtype=x.dtype, device=x.device)
         else:
@@ -146,10 +148,18 @@ class _ConvFn(torch.autograd.Function):
         if bias is not None:
             bias = _f32(bias).contiguous()
         engine = "simt"
-        flops = 2.0 * N * math.prod(O) * Cout * w.shape[0] * Cin
+        flops = 2.0 * N * math.prod(O) * Cout * w.shape[0] * Cin * flop_scale      # algorithmic (structural zeros not counted)
         if _use_umma(d, x, planar_out, N * math.prod(O)):
             from . import umma
-            umma.conv_fwd(x, w, bias, y, d, flops)
+            rows = 0
+            if stats_slot is not None and STATS_IN_EPILOGUE and act == ACT_NONE and not planar_out:
+                rows = int(_lib.lib().dfmir_conv_umma_stat_rows(ctypes.byref(d)))
+            if rows > 0:
+                stats_slot.rows = torch.empty((N, rows, Cout, 2), dtype=x.dtype, device=x.device)
+                stats_slot.rows_per_image = rows
+                umma.conv_fwd(x, w, bias, y, d, flops, stat_rows=stats_slot.rows)
+            else:
+                umma.conv_fwd(x, w, bias, y, d, flops)
             engine = "umma"
         else:
             _run(lambda: _lib.call("dfmir_conv_fwd", x, w, bias, y, ctypes.byref(d)), flops)
@@ -214,7 +224,7 @@ class _ConvFn(torch.autograd.Function):
                 _run(lambda: _lib.call("dfmir_conv_wgrad", x, dy, dw, db, ctypes.byref(d)), flops)
             if db_given is not None:
                 db = db_given if has_bias else None
-        return dx, dw, db, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None, None, None
 
 
 def _backward_padded_head(ctx, x, w, dy):
@@ -239,7 +249,7 @@ def _backward_padded_head(ctx, x, w, dy):
         umma.conv_wgrad(x, dyp, dwp, None, d, flops)
         dw = dwp[..., :Cout].contiguous()
         db = dy.sum(dim=[0] + list(range(2, nd + 2))) if has_bias else None
-    return dx, dw, db, None, None, None, None, None
+    return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 _ConvFn._backward_padded_head = staticmethod(_backward_padded_head)
@@ -299,6 +309,20 @@ class BiasGradSlot:
         self.db = None
 
 
+class StatsSlot:
+    """Hand-over of InstanceNorm statistics from the convolution in front of it: the tensor-core forward kernel sums its
+    result per channel while 32-voxel blocks are in registers (dfmir_conv_umma_fwd_stats) and parks the row sums here;
+    instnorm_cl(..., stats_slot=) reduces them (dfmir_instnorm_fwd_rows) instead of reading the whole tensor again.
+    Forward-only: the norm's backward is unchanged."""
+    __slots__ = ("rows", "rows_per_image")
+
+    def __init__(self):
+        self.rows, self.rows_per_image = None, 0
+
+
+STATS_IN_EPILOGUE = os.environ.get("DFMIR_IN_STATS_EPILOGUE", "1") != "0"
+
+
 class ResidualGradSlot:
     """Hand-over of the residual branch's gradient inside a ResnetBlock (out = x + conv_block(x)): the last
     InstanceNorm's backward writes d(out)/d(x) of the skip connection into a buffer shaped like the block input and
@@ -311,20 +335,102 @@ class ResidualGradSlot:
         self.dres = None
 
 
-def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False, bias_slot=None, res_slot=None):
+class _S2DFn(torch.autograd.Function):
+    """x (N,*S,C) -> (N,*S/2, 2^nd * C): channel = parity(d,h,w) * C + c  (dfmir_space_to_depth)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _lib.require_cuda(x)
+        x = _f32(x).contiguous()
+        nd = x.dim() - 2
+        O = [s // 2 for s in x.shape[1:1 + nd]]
+        C = x.shape[-1]
+        y = torch.empty((x.shape[0], *O, (1 << nd) * C), dtype=x.dtype, device=x.device)
+        _lib.call("dfmir_space_to_depth", x, y, x.shape[0], nd, O, C, 0)
+        ctx.meta = (tuple(x.shape), nd, O, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, nd, O, C = ctx.meta
+        dy = _f32(dy).contiguous()
+        dx = torch.empty(shape, dtype=dy.dtype, device=dy.device)
+        _lib.call("dfmir_space_to_depth", dy, dx, shape[0], nd, O, C, 1)
+        return dx
+
+
+def space_to_depth_cl(x):
+    return _S2DFn.apply(x)
+
+
+class _PackS2DFn(torch.autograd.Function):
+    """(Cout, Cin, 3^nd) parameter of a stride-2, pad-1 convolution -> kernel layout (2^nd taps, 2^nd * Cin, Cout) of the
+    equivalent stride-1 convolution over the space-to-depth activation: tap k of an axis sits at (t, p) with
+    k + 1 = 2 t + p, the slot (t, p) = (0, 0) is a structural zero."""
+
+    @staticmethod
+    def forward(ctx, weight):
+        Cout, Cin = weight.shape[:2]
+        nd = weight.dim() - 2
+        w4 = torch.nn.functional.pad(weight, (1, 0) * nd)                     # (Cout, Cin, 4, ...): index k + 1
+        w4 = w4.reshape(Cout, Cin, *([2, 2] * nd))                            # (.., t_a, p_a, ..)
+        t_axes = [2 + 2 * a for a in range(nd)]
+        p_axes = [3 + 2 * a for a in range(nd)]
+        w = w4.permute(*t_axes, *p_axes, 1, 0).reshape(1 << nd, (1 << nd) * Cin, Cout)
+        ctx.meta = (tuple(weight.shape), nd, id(weight))
+        return w.contiguous()
+
+    @staticmethod
+    def backward(ctx, dw):
+        shape, nd, key = ctx.meta
+        _pack_cache.pop((key, "s2d"), None)
+        Cout, Cin = shape[:2]
+        g = dw.reshape(*([2] * nd), *([2] * nd), Cin, Cout)                    # (t.., p.., Cin, Cout)
+        order = [2 * nd + 1, 2 * nd]
+        for a in range(nd):
+            order += [a, nd + a]
+        g = g.permute(*order).reshape(Cout, Cin, *([4] * nd))
+        return g[(slice(None), slice(None)) + (slice(1, None),) * nd]
+
+
+def packed_weight_s2d(weight):
+    grad = torch.is_grad_enabled() and weight.requires_grad
+    key = (id(weight), "s2d")
+    hit = _pack_cache.get(key)
+    if hit is not None:
+        ref, version, pad, g, w = hit
+        if ref() is weight and version == weight._version and g == grad:
+            return w
+    w = _PackS2DFn.apply(weight)
+    _pack_cache[key] = (weakref.ref(weight), weight._version, 0, grad, w)
+    return w
+
+
+# stride-2 3^nd encoder layers as stride-1 2^nd convolutions over the space-to-depth activation (tensor-core engine)
+S2D_STRIDED = os.environ.get("DFMIR_S2D_STRIDED", "1") != "0"
+
+
+def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False, bias_slot=None, res_slot=None, stats_slot=None):
     """Convolution on a channels-last activation with a PyTorch-layout weight (Cout, Cin, *k).
     Returns (N,*O,Cout), or the planar (N,Cout,*O) when planar_out."""
     nd = weight.dim() - 2
     kernel = list(weight.shape[2:])
     pads = [pad] * nd if isinstance(pad, int) else list(pad)
     Cin = weight.shape[1]
+    S = list(x.shape[1:1 + nd])
+    if (stride == 2 and S2D_STRIDED and CONV_ENGINE != "simt" and kernel == [3] * nd and pads == [1] * nd
+            and all(s % 2 == 0 for s in S) and x.shape[-1] == Cin and weight.shape[0] % 4 == 0 and weight.shape[0] >= 16
+            and x.shape[0] * math.prod(S) // (1 << nd) >= UMMA_MIN_POSITIONS and not planar_out):
+        xs = space_to_depth_cl(x)
+        return _ConvFn.apply(xs, packed_weight_s2d(weight), bias, [2] * nd, 1, [1] * nd, act, False, bias_slot, res_slot,
+                             [s // 2 for s in S], 27.0 / 64.0 if nd == 3 else 9.0 / 16.0)
     w = packed_weight(weight, x.shape[-1] - Cin)
-    return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out, bias_slot, res_slot)
+    return _ConvFn.apply(x, w, bias, kernel, stride, pads, act, planar_out, bias_slot, res_slot, None, 1.0, stats_slot)
 
 
 class _InstNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, relu, out_pad, res_pad, eps, bias_slot=None, res_slot=None):
+    def forward(ctx, x, res, relu, out_pad, res_pad, eps, bias_slot=None, res_slot=None, stats_slot=None):
         ctx.bias_slot = bias_slot
         ctx.res_slot = res_slot if res is not None else None
         _lib.require_cuda(x)
@@ -336,10 +442,19 @@ class _InstNormFn(torch.autograd.Function):
                 raise _lib.DfmirError(f"instnorm: residual {tuple(res.shape)} does not match {tuple(x.shape)} pad {res_pad}")
         y = torch.empty((N, H + 2 * out_pad, W + 2 * out_pad, C), dtype=x.dtype, device=x.device)
         stats = torch.empty((N, C, 2), dtype=x.dtype, device=x.device)
-        nbytes = _lib.lib().dfmir_instnorm_workspace_bytes(N, C)
-        ws = workspace(nbytes, x.device)
-        _lib.call("dfmir_instnorm_fwd", x, res, y, stats, ws, _lib.size_t(ws.numel()), N, H, W, C, float(eps),
-                  int(relu), out_pad, res_pad)
+        rows = None
+        if stats_slot is not None and stats_slot.rows is not None:
+            rows, stats_slot.rows = stats_slot.rows, None
+            if tuple(rows.shape) != (N, stats_slot.rows_per_image, C, 2):
+                raise _lib.DfmirError(f"instnorm: statistic rows {tuple(rows.shape)} do not belong to {tuple(x.shape)}")
+        if rows is not None:
+            _lib.call("dfmir_instnorm_fwd_rows", x, res, y, stats, rows, rows.shape[1], N, H, W, C, float(eps), int(relu),
+                      out_pad, res_pad)
+        else:
+            nbytes = _lib.lib().dfmir_instnorm_workspace_bytes(N, C)
+            ws = workspace(nbytes, x.device)
+            _lib.call("dfmir_instnorm_fwd", x, res, y, stats, ws, _lib.size_t(ws.numel()), N, H, W, C, float(eps),
+                      int(relu), out_pad, res_pad)
         ctx.save_for_backward(x, stats)
         ctx.meta = (N, H, W, C, int(relu), out_pad, res_pad, res is not None)
         return y
@@ -367,12 +482,12 @@ class _InstNormFn(torch.autograd.Function):
             slot.db = dbias
         if ctx.res_slot is not None and dres is not None:
             ctx.res_slot.dres, dres = dres, None        # taken up by the block's first convolution backward
-        return dx, dres, None, None, None, None, None, None
+        return dx, dres, None, None, None, None, None, None, None
 
 
-def instnorm_cl(x, relu=False, out_pad=0, res=None, res_pad=0, eps=1e-5, bias_slot=None, res_slot=None):
+def instnorm_cl(x, relu=False, out_pad=0, res=None, res_pad=0, eps=1e-5, bias_slot=None, res_slot=None, stats_slot=None):
     """InstanceNorm2d(affine=False) [+ReLU] [+res] written with a reflected halo of width out_pad."""
-    return _InstNormFn.apply(x, res, relu, out_pad, res_pad, eps, bias_slot, res_slot)
+    return _InstNormFn.apply(x, res, relu, out_pad, res_pad, eps, bias_slot, res_slot, stats_slot)
 
 
 class _PadReflectFn(torch.autograd.Function):

@@ -144,10 +144,11 @@ class ResnetBlock(nn.Module):
         c1, c2 = self.conv_block[1], self.conv_block[5]
         s1, s2 = Fn.BiasGradSlot(), Fn.BiasGradSlot()      # conv bias gradients summed by the IN backward passes
         rs = Fn.ResidualGradSlot()                         # skip-connection gradient, completed by c1's data gradient
-        y = Fn.conv_cl(P, c1.weight, c1.bias, bias_slot=s1, res_slot=rs)
-        P1 = Fn.instnorm_cl(y, relu=True, out_pad=1, bias_slot=s1)
-        y = Fn.conv_cl(P1, c2.weight, c2.bias, bias_slot=s2)
-        return Fn.instnorm_cl(y, relu=False, out_pad=out_pad, res=P, res_pad=1, bias_slot=s2, res_slot=rs)
+        t1, t2 = Fn.StatsSlot(), Fn.StatsSlot()            # norm statistics summed by the convolution epilogues
+        y = Fn.conv_cl(P, c1.weight, c1.bias, bias_slot=s1, res_slot=rs, stats_slot=t1)
+        P1 = Fn.instnorm_cl(y, relu=True, out_pad=1, bias_slot=s1, stats_slot=t1)
+        y = Fn.conv_cl(P1, c2.weight, c2.bias, bias_slot=s2, stats_slot=t2)
+        return Fn.instnorm_cl(y, relu=False, out_pad=out_pad, res=P, res_pad=1, bias_slot=s2, res_slot=rs, stats_slot=t2)
 
     def forward(self, x):
         P = Fn.pad_reflect_cl(x.permute(0, 2, 3, 1), 1)
@@ -234,9 +235,9 @@ class ResnetGenerator(nn.Module):
             a = Fn.instnorm_cl(y, relu=True, bias_slot=sl); tap(2, a); tap(3, a)
             idx = 4
             for i in range(nd):
-                sl = slot(idx)
-                y = Fn.conv_cl(a, m[idx].weight, m[idx].bias, pad=1, bias_slot=sl); tap(idx, y)
-                a = Fn.instnorm_cl(y, relu=True, bias_slot=sl); tap(idx + 1, a); tap(idx + 2, a)
+                sl, st = slot(idx), Fn.StatsSlot()
+                y = Fn.conv_cl(a, m[idx].weight, m[idx].bias, pad=1, bias_slot=sl, stats_slot=st); tap(idx, y)
+                a = Fn.instnorm_cl(y, relu=True, bias_slot=sl, stats_slot=st); tap(idx + 1, a); tap(idx + 2, a)
                 a = Fn.blur_down_cl(a); tap(idx + 3, a)
                 idx += 4
             if nb > 0:
@@ -248,10 +249,10 @@ class ResnetGenerator(nn.Module):
                 a = P
             for i in range(nd):
                 a = Fn.blur_up_cl(a); tap(idx, a)
-                sl = slot(idx + 1)
-                y = Fn.conv_cl(a, m[idx + 1].weight, m[idx + 1].bias, pad=1, bias_slot=sl); tap(idx + 1, y)
+                sl, st = slot(idx + 1), Fn.StatsSlot()
+                y = Fn.conv_cl(a, m[idx + 1].weight, m[idx + 1].bias, pad=1, bias_slot=sl, stats_slot=st); tap(idx + 1, y)
                 op = 3 if i + 1 == nd else 0
-                a = Fn.instnorm_cl(y, relu=True, out_pad=op, bias_slot=sl); tap(idx + 2, interior(a, op)); tap(idx + 3, interior(a, op))
+                a = Fn.instnorm_cl(y, relu=True, out_pad=op, bias_slot=sl, stats_slot=st); tap(idx + 2, interior(a, op)); tap(idx + 3, interior(a, op))
                 idx += 4
             tap(idx, a)                                     # ReflectionPad2d(3) output
             if (idx + 1) in want:

@@ -44,8 +44,12 @@ def _kmajor(w):
     return wk
 
 
-def conv_fwd(x, w, bias, y, d, flops=0.0):
+def conv_fwd(x, w, bias, y, d, flops=0.0, stat_rows=None):
     wk = _kmajor(w)
+    if stat_rows is not None:       # InstanceNorm statistics of y as a by-product of the epilogue
+        _run(lambda: _lib.call("dfmir_conv_umma_fwd_stats", x, wk, bias, y, ctypes.byref(d), stat_rows), flops, "umma_fwd",
+             _nbytes(x, wk, y))
+        return
     _run(lambda: _lib.call("dfmir_conv_umma_fwd", x, wk, bias, y, ctypes.byref(d)), flops, "umma_fwd", _nbytes(x, wk, y))
 
 

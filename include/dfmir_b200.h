@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DFMIR_ABI_VERSION 5
+#define DFMIR_ABI_VERSION 6
 
 #define DFMIR_INTERP_LINEAR 0
 #define DFMIR_INTERP_NEAREST 1
@@ -139,6 +139,13 @@ int dfmir_conv_dgrad(const float* dy, const float* wt, float* dx, const dfmir_co
 int dfmir_conv_umma_supported(const dfmir_conv_desc* d, int dgrad);
 int dfmir_conv_umma_fwd(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
                         void* stream);
+/* Forward with the InstanceNorm statistics of its result as an epilogue by-product (models/networks.py:984,996,1020,
+ * 1201-1215: InstanceNorm2d follows every generator convolution): stat_rows receives [N][rows][Cout] float2 {sum, sum of
+ * squares} over row groups of <= 32 voxels; dfmir_instnorm_fwd_rows consumes them.  dfmir_conv_umma_stat_rows: rows per
+ * image for this shape, 0 when the kernel chosen for it has no such epilogue. */
+int dfmir_conv_umma_stat_rows(const dfmir_conv_desc* d);
+int dfmir_conv_umma_fwd_stats(const float* x, const float* w, const float* bias, float* y, const dfmir_conv_desc* d,
+                              float* stat_rows, void* stream);
 int dfmir_conv_umma_dgrad(const float* dy, const float* w, float* dx, const dfmir_conv_desc* d, void* stream);
 /* dx += data gradient (the ResnetBlock input already holds the residual branch's gradient, models/networks.py:1218-1221):
  * covered by the CTA-pair kernel (2-D 3x3, Cin a multiple of 256); _supported tells, else DFMIR_ERR_UNSUPPORTED. */
@@ -163,6 +170,10 @@ int dfmir_act_bwd(const float* y, const float* dy, float* dx, long long n, int a
 size_t dfmir_instnorm_workspace_bytes(int N, int C);
 int dfmir_instnorm_fwd(const float* x, const float* res, float* y, float* stats, void* ws, size_t ws_bytes, int N,
                        int H, int W, int C, float eps, int relu, int out_pad, int res_pad, void* stream);
+/* Same layer, statistics reduced from the row sums written by dfmir_conv_umma_fwd_stats (no pass over x for them) */
+int dfmir_instnorm_fwd_rows(const float* x, const float* res, float* y, float* stats, const float* stat_rows,
+                            int rows_per_image, int N, int H, int W, int C, float eps, int relu, int out_pad, int res_pad,
+                            void* stream);
 /* dy (N,H+2p,W+2p,C) -> dx (N,H,W,C); dres (nullable, (N,H+2rp,W+2rp,C), halo zeroed here) */
 int dfmir_instnorm_bwd(const float* dy, const float* x, const float* stats, float* dx, float* dres, void* ws,
                        size_t ws_bytes, int N, int H, int W, int C, int relu, int out_pad, int res_pad,
@@ -181,6 +192,11 @@ int dfmir_blur_down_fwd(const float* x, float* y, int N, int H, int W, int C, vo
 int dfmir_blur_down_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
 int dfmir_blur_up_fwd(const float* x, float* y, int N, int H, int W, int C, void* stream);
 int dfmir_blur_up_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream);
+/* ---- space-to-depth view of a channels-last activation: the stride-2 3^nd encoder convolutions of VoxelMorph's U-Net
+ * (vxm networks.py:1514-1515, ConvBlock stride=2; Unet.downarm :52-56) become stride-1 2^nd convolutions over it and run
+ * on the tcgen05 kernels.  src (N,*2*out_shape,C) -> dst (N,*out_shape,2^nd*C), channel = parity(d,h,w)*C + c;
+ * inverse != 0: the inverse permutation (= the adjoint, used for the data gradient). */
+int dfmir_space_to_depth(const float* src, float* dst, int N, int nd, const int* out_shape, int C, int inverse, void* stream);
 /* ---- nn.Upsample(x2, nearest) + torch.cat([x, skip], 1) — vxm networks.py:99-102; channels-last.
  * a (N,*shape/2,C1), b (N,*shape,C2) -> y (N,*shape,C1+C2) */
 int dfmir_upsample_concat_fwd(const float* a, const float* b, float* y, int N, int nd, const int* shape, int C1,

@@ -74,7 +74,7 @@ def test_loadable_model_round_trip(tmp_path):
     ck = torch.load(path)
     assert set(ck.keys()) == {"config", "model_state"} and not any(k.endswith(".grid") for k in ck["model_state"])
     assert ck["config"]["inshape"] == (32, 48) and ck["config"]["int_steps"] == 5 and ck["config"]["bidir"] is True
-    R2 = vxm.VxmDense.load(path, "cuda")
+    R2 = vxm.VxmDense.load(path, "cuda").cuda()        # like the reference, load() builds the module on the CPU
     a, b = R.state_dict(), R2.state_dict()
     assert list(a.keys()) == list(b.keys())
     for k in a:
