@@ -1129,7 +1129,29 @@ tf32_split3_kernel(const float* __restrict__ x, float* __restrict__ out, long lo
     o[0] = hi; o[D] = b_style ? lo : hi; o[2 * D] = b_style ? hi : lo;
   }
 }
+// the same split stacked along the rows, for products that reduce over the rows (weight gradients): out (3, rows, D),
+// a-style [hi ; hi ; lo], b-style [hi ; lo ; hi]
+__global__ void __launch_bounds__(256)
+tf32_split3_rows_kernel(const float* __restrict__ x, float* __restrict__ out, long long total, int b_style) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const float lo = v - hi;
+    out[i] = hi; out[total + i] = b_style ? lo : hi; out[2 * total + i] = b_style ? hi : lo;
+  }
+}
 }  // namespace
+
+extern "C" int dfmir_tf32_split3_rows(const float* x, float* out, long long rows, int D, int b_style, void* stream) {
+  DFMIR_CHECK_ARG(x && out && rows >= 0 && D > 0, "dfmir_tf32_split3_rows: bad argument");
+  const long long total = rows * D;
+  if (total == 0) return DFMIR_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)dfmir_num_sms() * 16;
+  tf32_split3_rows_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(x, out, total, b_style);
+  DFMIR_CHECK_LAUNCH("dfmir_tf32_split3_rows");
+  return DFMIR_OK;
+}
 
 extern "C" int dfmir_tf32_split3(const float* x, float* out, long long rows, int D, int b_style, void* stream) {
   DFMIR_CHECK_ARG(x && out && rows >= 0 && D > 0, "dfmir_tf32_split3: bad argument");

@@ -628,15 +628,75 @@ class _LinearFn(torch.autograd.Function):
         return dx, dW, db, None
 
 
+def _split3_rows(x, b_style):
+    rows, D = x.shape
+    out = torch.empty((3 * rows, D), dtype=x.dtype, device=x.device)
+    _lib.call("dfmir_tf32_split3_rows", x, out, _lib.i64(rows), D, int(b_style))
+    return out
+
+
+class _LinearTCFn(torch.autograd.Function):
+    """nn.Linear on the tensor cores at fp32-class accuracy (the reference's nn.Linear is plain fp32: torch.matmul does
+    not use TF32 by default): every product runs on the tcgen05 kernels with 3xTF32-split operands (hi*hi + hi*lo +
+    lo*hi, models/networks.py:587-595 create_mlp).  A row-major (M, K) x (N, K)^T product IS a 1x1 convolution over M
+    pixels: forward and dx on conv_umma_kernel (split along the reduction = channel axis), dW on the split-K
+    weight-gradient kernel (split along the reduction = pixel axis)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        _lib.require_cuda(x, W)
+        x, W = _f32(x).contiguous(), _f32(W).contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        y = torch.empty((M, N), dtype=x.dtype, device=x.device)
+        xs, Ws = _split3(x, False), _split3(W, True)
+        d = _make_desc(2, 1, 3 * K, N, [M // 64, 64], [M // 64, 64], [1, 1], [0, 0], 1, ACT_RELU if relu else ACT_NONE,
+                       [M * 3 * K, 64 * 3 * K, 3 * K, 1], [M * N, 64 * N, N, 1])
+        _run(lambda: _lib.call("dfmir_conv_umma_fwd", xs, Ws, b, y, ctypes.byref(d)), 2.0 * M * N * K, "umma_fwd", _nbytes(xs, Ws, y))
+        ctx.save_for_backward(x, W, y if relu else None)
+        ctx.meta = (M, N, K, relu, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        M, N, K, relu, has_b = ctx.meta
+        dy = _f32(dy).contiguous()
+        if relu:
+            g = torch.empty_like(dy)
+            _lib.call("dfmir_act_bwd", y, dy, g, _lib.i64(y.numel()), ACT_RELU)
+            dy = g
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            dys, WTs = _split3(dy, False), _split3(W.t().contiguous(), True)        # (M, 3N), (K, 3N)
+            d = _make_desc(2, 1, 3 * N, K, [M // 64, 64], [M // 64, 64], [1, 1], [0, 0], 1, ACT_NONE,
+                           [M * 3 * N, 64 * 3 * N, 3 * N, 1], [M * K, 64 * K, K, 1])
+            _run(lambda: _lib.call("dfmir_conv_umma_fwd", dys, WTs, None, dx, ctypes.byref(d)), 2.0 * M * N * K, "umma_dgrad",
+                 _nbytes(dys, WTs, dx))
+        if ctx.needs_input_grad[1]:
+            x3, dy3 = _split3_rows(x, False), _split3_rows(dy, True)                 # (3M, K), (3M, N)
+            dw = torch.zeros((1, K, N), dtype=x.dtype, device=x.device)
+            d = _make_desc(2, 1, K, N, [3 * M // 64, 64], [3 * M // 64, 64], [1, 1], [0, 0], 1, ACT_NONE,
+                           [3 * M * K, 64 * K, K, 1], [3 * M * N, 64 * N, N, 1])
+            _run(lambda: _lib.call("dfmir_conv_umma_wgrad", x3, dy3, dw, None, ctypes.byref(d)), 2.0 * M * N * K, "umma_wgrad",
+                 _nbytes(x3, dy3, dw))
+            dW = dw.view(K, N).t()
+        if has_b and ctx.needs_input_grad[2]:
+            ones = torch.ones(M, dtype=dy.dtype, device=dy.device)
+            db = torch.empty(N, dtype=dy.dtype, device=dy.device)
+            gemm(ones, dy, db, 1, N, M, (0, M, 1), (0, N, 1), (0, N, 1))
+        return dx, dW, db, None
+
+
 def linear(x, W, b, relu=False):
-    """y = relu?(x W^T + b).  On the tensor-core engine a row-major (M, K) x (N, K)^T product IS a 1x1 convolution
-    over M pixels with K input and N output channels: large ones (the PatchSampleF MLP at 4096+ rows) run on
-    conv_umma_kernel (forward, dx and dW), the rest on the fp32 GEMM kernel."""
+    """y = relu?(x W^T + b): large products (the PatchSampleF MLP at 4096+ rows) on the tensor cores with 3xTF32-split
+    operands (_LinearTCFn), the rest on the fp32 GEMM kernel - fp32-class accuracy either way, like nn.Linear."""
     M, K = x.shape
-    if (CONV_ENGINE != "simt" and M >= UMMA_MIN_POSITIONS and M % 64 == 0 and K % 4 == 0 and K >= 16
-            and x.is_contiguous() and x.data_ptr() % 16 == 0):
-        y = conv_cl(x.view(1, M // 64, 64, K), W.view(W.shape[0], K, 1, 1), b, act=ACT_RELU if relu else ACT_NONE)
-        return y.view(M, W.shape[0])
+    N = W.shape[0]
+    if (CONV_ENGINE != "simt" and M >= UMMA_MIN_POSITIONS and M % 64 == 0 and K % 4 == 0 and K >= 16 and N % 4 == 0 and N >= 16
+            and x.data_ptr() % 16 == 0):
+        return _LinearTCFn.apply(x, W, b, relu)
     return _LinearFn.apply(x, W, b, relu)
 
 

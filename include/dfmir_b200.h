@@ -221,6 +221,8 @@ int dfmir_patchnce_bwd(const float* S, const float* k, const float* g, float* wo
  * dfmir_tf32_split3: x (rows, D) -> out (rows, 3D), a-style [hi|hi|lo] or b-style [hi|lo|hi].
  * dfmir_bmm_nt_umma: C[b] (M,N) = A[b] (M,K) * B[b]^T (N,K), dense row-major, M % 256 == 0 (N > 64), K % 4 == 0. */
 int dfmir_tf32_split3(const float* x, float* out, long long rows, int D, int b_style, void* stream);
+/* the same split stacked along the rows (out (3, rows, D)), for products that reduce over the rows (dW = dy^T x) */
+int dfmir_tf32_split3_rows(const float* x, float* out, long long rows, int D, int b_style, void* stream);
 int dfmir_bmm_nt_umma(const float* A, const float* B, float* C, int batch, int M, int N, int K, void* stream);
 int dfmir_patchnce_tc_fwd(const float* q3, const float* k3, float* S, float* loss, int B, int P, int D3, float T,
                           void* stream);

@@ -542,3 +542,34 @@ def test_instnorm_statistics_from_conv_epilogue(N, Cin, Cout, H, W, pad):
     # backward: the norm's output gradient feeds a TF32 data-gradient product; 1e-7 differences in the statistics move
     # a few operands across a truncation boundary (2^-11 relative each)
     assert float((out[True][1] - out[False][1]).abs().max()) <= 2e-4 * float(out[False][1].abs().max()) + 1e-7
+
+
+@pytest.mark.parametrize("M,K,N,relu", [(4096, 256, 256, True), (4096, 128, 256, True), (8192, 256, 256, False)])
+def test_linear_on_tensor_cores_is_fp32_class(M, K, N, relu):
+    """PatchSampleF's nn.Linear layers (models/networks.py:587-595) at >= 4096 rows run on the tcgen05 kernels with
+    3xTF32-split operands: forward, dx, dW and db agree with float64 to fp32 accuracy (1e-5 of the scale; plain TF32
+    would be ~1e-3), because the reference's nn.Linear is an fp32 product."""
+    import dfmir_b200.functional as Fn
+    r = gi.rng(1700 + K + N)
+    x = torch.from_numpy(r.standard_normal((M, K)).astype(np.float32))
+    W = torch.from_numpy((r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32))
+    b = torch.from_numpy(r.standard_normal(N).astype(np.float32))
+    gy = torch.from_numpy(r.standard_normal((M, N)).astype(np.float32))
+    xr, Wr, br = x.double().requires_grad_(), W.double().requires_grad_(), b.double().requires_grad_()
+    yr = torch.nn.functional.linear(xr, Wr, br)
+    if relu:
+        yr = torch.relu(yr)
+    yr.backward(gy.double())
+    prof = Fn.ConvProfile(); Fn.PROFILE = prof
+    try:
+        xg, Wg, bg = x.cuda().requires_grad_(), W.cuda().requires_grad_(), b.cuda().requires_grad_()
+        y = Fn.linear(xg, Wg, bg, relu=relu)
+        y.backward(gy.cuda())
+        torch.cuda.synchronize()
+    finally:
+        Fn.PROFILE = None
+    assert set(prof.by_kind()) == {"umma_fwd", "umma_dgrad", "umma_wgrad"}, prof.by_kind().keys()
+    for name, got, want in (("y", y.detach(), yr.detach()), ("dx", xg.grad, xr.grad), ("dW", Wg.grad, Wr.grad), ("db", bg.grad, br.grad)):
+        sc = float(want.abs().max())
+        err = float((got.cpu().double() - want).abs().max())
+        assert err <= 1e-5 * sc, (name, err, sc)

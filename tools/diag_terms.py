@@ -54,40 +54,52 @@ for k, t in o_terms.items():
     o_g[k] = [None if g is None else g.detach() for g in gs]
     print("oracle", k, float(t))
 
-# ---------------- ours
-opt = rm.default_options(batch_size=B, crop_size=S, load_size=S, gpu_ids=[0])
-with contextlib.redirect_stdout(io.StringIO()):
-    m = rm.REGISTRATIONModel(opt)
-    m.data_dependent_initialize({'A': A, 'B': Bm})
-    m.setup(opt)
-for n, sd in zip('GFR', sds):
-    getattr(m, 'net' + n).load_state_dict(sd, strict=False)
-m.set_input({'A': A, 'B': Bm})
-m.forward()
-y = m.netR(m.real_A, m.real_B)
-flow = y[2]
-m.registered = m.spatialTransformer(m.fake_B, flow)
-m.regA = y[0]
-dev = m.device
-terms = {
-    'NCE': m.calculate_NCE_loss(m.real_A, m.fake_B, [t.to(dev) for t in ids_for(0)]),
-    'NCE_Y': m.calculate_NCE_loss(m.real_B, m.idt_B, [t.to(dev) for t in ids_for(1)]),
-    'local': m.calculate_NCE_loss(m.real_B, m.regA, [t.to(dev) for t in ids_for(2)]) * 0.25,
-}
-la, lb = m._masked_l1_pair((m.registered, m.real_B, m.real_B, m.registered), (m.idt_B, m.registered, m.idt_B, m.registered))
-terms['L1a'], terms['L1b'] = la, lb
-terms['smooth'] = rm.smooothing_loss(flow) * 0.2
-w4 = m.netG.model[4].weight
-for k, t in terms.items():
-    gs = torch.autograd.grad(t, [m.fake, flow, w4], retain_graph=True, allow_unused=True)
-    line = f"{k:7s} ours {float(t):.6f} oracle {float(o_terms[k]):.6f}"
-    for name, g, ref in zip(("d/dfake", "d/dflow", "d/dw4"), gs, o_g[k]):
-        if g is None or ref is None:
-            continue
-        g = g.detach().cpu().double()
-        if g.is_sparse:
-            g = g.to_dense()
-        rel = float((g - ref).norm() / (ref.norm() + 1e-300))
-        cos = float((g * ref).sum() / (g.norm() * ref.norm() + 1e-300))
-        line += f" | {name} |ref| {float(ref.norm()):.3e} relerr {rel:.3e} cos {cos:.5f}"
-    print(line)
+# ---------------- ours, under several switches
+def run_ours(tag):
+    opt = rm.default_options(batch_size=B, crop_size=S, load_size=S, gpu_ids=[0])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = rm.REGISTRATIONModel(opt)
+        m.data_dependent_initialize({'A': A, 'B': Bm})
+        m.setup(opt)
+    for n, sd in zip('GFR', sds):
+        getattr(m, 'net' + n).load_state_dict(sd, strict=False)
+    m.set_input({'A': A, 'B': Bm})
+    m.forward()
+    y = m.netR(m.real_A, m.real_B)
+    flow = y[2]
+    m.registered = m.spatialTransformer(m.fake_B, flow)
+    m.regA = y[0]
+    dev = m.device
+    terms = {
+        'NCE': m.calculate_NCE_loss(m.real_A, m.fake_B, [t.to(dev) for t in ids_for(0)]),
+        'NCE_Y': m.calculate_NCE_loss(m.real_B, m.idt_B, [t.to(dev) for t in ids_for(1)]),
+        'local': m.calculate_NCE_loss(m.real_B, m.regA, [t.to(dev) for t in ids_for(2)]) * 0.25,
+    }
+    la, lb = m._masked_l1_pair((m.registered, m.real_B, m.real_B, m.registered), (m.idt_B, m.registered, m.idt_B, m.registered))
+    terms['L1a'], terms['L1b'] = la, lb
+    terms['smooth'] = rm.smooothing_loss(flow) * 0.2
+    w4 = m.netG.model[4].weight
+    for k, t in terms.items():
+        gs = torch.autograd.grad(t, [m.fake, flow, w4], retain_graph=True, allow_unused=True)
+        line = f"[{tag}] {k:7s} ours {float(t):.6f} oracle {float(o_terms[k]):.6f}"
+        for name, g, ref in zip(("d/dfake", "d/dflow", "d/dw4"), gs, o_g[k]):
+            if g is None or ref is None:
+                continue
+            g = g.detach().cpu().double()
+            if g.is_sparse:
+                g = g.to_dense()
+            rel = float((g - ref).norm() / (ref.norm() + 1e-300))
+            cos = float((g * ref).sum() / (g.norm() * ref.norm() + 1e-300))
+            line += f" | {name} |ref| {float(ref.norm()):.3e} relerr {rel:.3e} cos {cos:.5f}"
+        print(line)
+
+
+for tag, setup in [("default", lambda: None),
+                   ("dense_tap_grad", lambda: setattr(Fn, "SPARSE_TAP_GRAD", False)),
+                   ("no_stats_epilogue", lambda: setattr(Fn, "STATS_IN_EPILOGUE", False)),
+                   ("no_s2d", lambda: setattr(Fn, "S2D_STRIDED", False)),
+                   ("no_reuse", lambda: setattr(rm, "REUSE_REAL_FEATURES", False)),
+                   ("simt", lambda: setattr(Fn, "CONV_ENGINE", "simt"))]:
+    Fn.SPARSE_TAP_GRAD, Fn.STATS_IN_EPILOGUE, Fn.S2D_STRIDED, rm.REUSE_REAL_FEATURES, Fn.CONV_ENGINE = True, True, True, True, "auto"
+    setup()
+    run_ours(tag)
