@@ -645,6 +645,77 @@ upcat_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float
   }
 }
 
+// 128-bit variant (C1 % 4 == 0, Cs % 4 == 0): one float4 of one output voxel per thread.  The first C1 / 4 quads are
+// copies of the parent voxel's quads; the remaining ones are assembled from the skip tensor (whole quads when C2 % 4 == 0)
+// and the zero padding.
+__global__ void __launch_bounds__(256)
+upcat_fwd_v4_kernel(const float4* __restrict__ a, const float* __restrict__ b, float4* __restrict__ y, UcGeom g) {
+  const int Q = g.Cs >> 2, Q1 = g.C1 >> 2;
+  const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
+  const long long total = (long long)g.N * vox * Q;
+  const int L0 = g.S[0] > 1 ? g.S[0] / 2 : 1, L1 = g.S[1] / 2, L2 = g.S[2] / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / Q;
+    const int j = (int)(i - pix * Q);
+    float4 v;
+    if (j < Q1) {
+      long long q = pix;
+      const int xw = (int)(q % g.S[2]); q /= g.S[2];
+      const int yh = (int)(q % g.S[1]); q /= g.S[1];
+      const int zd = (int)(q % g.S[0]); q /= g.S[0];
+      const int lz = g.S[0] > 1 ? zd >> 1 : 0;
+      v = a[((((q * L0 + lz) * L1 + (yh >> 1)) * L2 + (xw >> 1)) * Q1) + j];
+    } else {
+      const int c0 = (j << 2) - g.C1;              // first skip channel of this quad
+      const float* bp = b + pix * g.C2 + c0;
+      if ((g.C2 & 3) == 0 && c0 + 4 <= g.C2) {
+        v = *reinterpret_cast<const float4*>(bp);
+      } else {
+        v.x = c0 < g.C2 ? bp[0] : 0.f; v.y = c0 + 1 < g.C2 ? bp[1] : 0.f;
+        v.z = c0 + 2 < g.C2 ? bp[2] : 0.f; v.w = c0 + 3 < g.C2 ? bp[3] : 0.f;
+      }
+    }
+    y[i] = v;
+  }
+}
+
+// da (128-bit, C1 % 4 == 0, Cs % 4 == 0): one quad of one parent voxel per thread, the 2^nd children summed in a fixed order
+__global__ void __launch_bounds__(256)
+upcat_bwd_a_v4_kernel(const float4* __restrict__ dy, float4* __restrict__ da, UcGeom g) {
+  const int Q = g.Cs >> 2, Q1 = g.C1 >> 2;
+  const int L0 = g.S[0] > 1 ? g.S[0] / 2 : 1, L1 = g.S[1] / 2, L2 = g.S[2] / 2;
+  const long long total = (long long)g.N * L0 * L1 * L2 * Q1;
+  const int nz = g.S[0] > 1 ? 2 : 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long q = i;
+    const int j = (int)(q % Q1); q /= Q1;
+    const int lx = (int)(q % L2); q /= L2;
+    const int ly = (int)(q % L1); q /= L1;
+    const int lz = (int)(q % L0); q /= L0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int dz = 0; dz < nz; ++dz)
+#pragma unroll
+      for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+        for (int dxx = 0; dxx < 2; ++dxx) {
+          const int zd = g.S[0] > 1 ? 2 * lz + dz : 0;
+          const float4 t = dy[((((q * g.S[0] + zd) * g.S[1] + 2 * ly + dyy) * g.S[2] + 2 * lx + dxx) * Q) + j];
+          acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+    da[i] = acc;
+  }
+}
+
+// db = dy[..., C1 : C1 + C2]
+__global__ void __launch_bounds__(256)
+upcat_bwd_b_kernel(const float* __restrict__ dy, float* __restrict__ db, long long pixels, int C1, int C2, int Cs) {
+  const long long total = pixels * C2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C2;
+    db[i] = dy[pix * Cs + C1 + (int)(i - pix * C2)];
+  }
+}
+
 // da = sum over the 2^nd children of dy[..., :C1];  db = dy[..., C1:]
 __global__ void __launch_bounds__(256)
 upcat_bwd_kernel(const float* __restrict__ dy, float* __restrict__ da, float* __restrict__ db, UcGeom g) {
@@ -925,7 +996,10 @@ extern "C" int dfmir_upsample_concat_padded_fwd(const float* a, const float* b, 
   DFMIR_CHECK_ARG(Cs >= C1 + C2, "dfmir_upsample_concat_fwd: channel stride %d smaller than %d + %d channels", Cs, C1, C2);
   g.Cs = Cs;
   const long long total = (long long)N * g.S[0] * g.S[1] * g.S[2] * Cs;
-  upcat_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(a, b, y, g);
+  if (C1 % 4 == 0 && Cs % 4 == 0 && ((((uintptr_t)a) | ((uintptr_t)y)) & 15) == 0 && (C2 % 4 != 0 || (((uintptr_t)b) & 15) == 0))
+    upcat_fwd_v4_kernel<<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)a, b, (float4*)y, g);
+  else
+    upcat_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(a, b, y, g);
   DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_fwd");
   return DFMIR_OK;
 }
@@ -939,7 +1013,15 @@ extern "C" int dfmir_upsample_concat_padded_bwd(const float* dy, float* da, floa
   g.Cs = Cs;
   const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
   const long long total = (long long)N * (vox >> nd) * C1 + (long long)N * vox * C2;
-  upcat_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dy, da, db, g);
+  if (C1 % 4 == 0 && Cs % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)da)) & 15) == 0) {
+    if (da) upcat_bwd_a_v4_kernel<<<ew_grid((long long)N * (vox >> nd) * (C1 / 4)), 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (float4*)da, g);
+    if (db && C2 > 0) {
+      if (da) DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_bwd");
+      upcat_bwd_b_kernel<<<ew_grid((long long)N * vox * C2), 256, 0, (cudaStream_t)stream>>>(dy, db, (long long)N * vox, C1, C2, Cs);
+    }
+  } else {
+    upcat_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(dy, da, db, g);
+  }
   DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_bwd");
   return DFMIR_OK;
 }

@@ -21,6 +21,15 @@ CONV_ENGINE = os.environ.get("DFMIR_CONV_ENGINE", "auto")
 # layers with fewer output positions than this stay on the fp32 kernels (launch-bound; TMA descriptor set-up
 # would dominate).  Tests set it to 0 to drive small shapes through the tensor-core kernels.
 UMMA_MIN_POSITIONS = int(os.environ.get("DFMIR_UMMA_MIN_POSITIONS", "4096"))
+# ... unless their reduction is long: the deep U-Net levels (128 -> 64 channels, 3x3x3, at 8^3 / 4^3 voxels) have a few
+# hundred positions but K = 3456; the fp32 kernel runs them on 1 - 8 CTAs for ~0.3 ms each, the tensor-core kernel in a few us
+UMMA_MIN_K_SMALL = int(os.environ.get("DFMIR_UMMA_MIN_K_SMALL", "512"))
+UMMA_MIN_POSITIONS_SMALL = 16
+
+
+def _tc_size(positions, k_len):
+    """Layer big enough for the tensor-core kernels?  positions = output positions, k_len = reduction length."""
+    return positions >= UMMA_MIN_POSITIONS or (UMMA_MIN_POSITIONS > 0 and positions >= UMMA_MIN_POSITIONS_SMALL and k_len >= UMMA_MIN_K_SMALL)
 
 
 class ConvProfile:
@@ -116,7 +125,10 @@ def workspace(nbytes, device):
 
 def _use_umma(d, x, y_planar, positions):
     """Forward on the tensor cores?  (the backward products are decided one by one in _ConvFn.backward)"""
-    if CONV_ENGINE == "simt" or positions < UMMA_MIN_POSITIONS or x.data_ptr() % 16 or d.Cin == 1 or d.Cout == 1:
+    taps = 1
+    for i in range(d.nd):
+        taps *= d.kernel[i]
+    if CONV_ENGINE == "simt" or not _tc_size(positions, d.Cin * taps) or x.data_ptr() % 16 or d.Cin == 1 or d.Cout == 1:
         return False      # tiny layers are launch-bound; the 7x7 stem / head have their own exact direct kernels
     from . import umma
     return umma.supported(d, False)
@@ -182,7 +194,7 @@ class _ConvFn(torch.autograd.Function):
         dx = dw = db = None
         ys = _cl_strides(dy, nd, planar_out)
         # tensor-core engine, decided product by product (not for the stem / head: direct fp32 kernels)
-        tc = CONV_ENGINE != "simt" and N * math.prod(O) >= UMMA_MIN_POSITIONS and Cin != 1 and Cout != 1
+        tc = CONV_ENGINE != "simt" and _tc_size(N * math.prod(O), Cin * math.prod(kernel)) and Cin != 1 and Cout != 1
         if tc:
             from . import umma
         if tc and planar_out and Cout % 4 and stride == 1 and Cin % 4 == 0 and x.data_ptr() % 16 == 0:
@@ -420,7 +432,7 @@ def conv_cl(x, weight, bias, stride=1, pad=0, act=ACT_NONE, planar_out=False, bi
     S = list(x.shape[1:1 + nd])
     if (stride == 2 and S2D_STRIDED and CONV_ENGINE != "simt" and kernel == [3] * nd and pads == [1] * nd
             and all(s % 2 == 0 for s in S) and x.shape[-1] == Cin and weight.shape[0] % 4 == 0 and weight.shape[0] >= 16
-            and x.shape[0] * math.prod(S) // (1 << nd) >= UMMA_MIN_POSITIONS and not planar_out):
+            and _tc_size(x.shape[0] * math.prod(S) // (1 << nd), Cin * 3 ** nd) and not planar_out):
         xs = space_to_depth_cl(x)
         return _ConvFn.apply(xs, packed_weight_s2d(weight), bias, [2] * nd, 1, [1] * nd, act, False, bias_slot, res_slot,
                              [s // 2 for s in S], 27.0 / 64.0 if nd == 3 else 9.0 / 16.0)

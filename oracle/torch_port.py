@@ -29,9 +29,10 @@ _BLUR4 = torch.tensor([1., 3., 3., 1.])
 # ---- TF32 operand emulation (for checking the tcgen05 engine) -------------------------------------
 # The tensor core reads fp32 operands and keeps sign, exponent and the top 10 mantissa bits
 # (truncation: the low 13 bits are ignored); products are exact, accumulation is fp32.  With
-# TF32_EMULATION set, the convolutions the tensor-core engine covers (2-D, stride 1, Cin and Cout in
-# {64,128,256}) run forward / data-gradient / weight-gradient on truncated operands, in the given
-# accumulation dtype.  None (default) = plain F.conv2d, the reference's CPU arithmetic.
+# TF32_EMULATION set, the convolutions the tensor-core engine covers (generator: Cin and Cout in {64,128,256};
+# registration U-Net: Cin and Cout >= 16, 2-D / 3-D, stride 1 / 2) run forward / data-gradient / weight-gradient
+# on truncated operands, in the given accumulation dtype.  None (default) = plain F.conv{2,3}d, the reference's
+# CPU arithmetic.
 TF32_EMULATION = None      # None | "trunc" | "rna"
 
 
@@ -45,25 +46,40 @@ def tf32_round(t, mode="trunc"):
 
 
 class _Tf32Conv(torch.autograd.Function):
+    """conv{2,3}d on TF32-truncated operands, all three products (forward, data gradient, weight gradient)."""
+
     @staticmethod
-    def forward(ctx, x, w, b, padding):
+    def forward(ctx, x, w, b, padding, stride):
         ctx.save_for_backward(x, w)
-        ctx.padding = padding
-        return F.conv2d(tf32_round(x, TF32_EMULATION), tf32_round(w, TF32_EMULATION), b, padding=padding)
+        ctx.padding, ctx.stride = padding, stride
+        conv = F.conv2d if x.dim() == 4 else F.conv3d
+        return conv(tf32_round(x, TF32_EMULATION), tf32_round(w, TF32_EMULATION), b, stride=stride, padding=padding)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gq, xq, wq = tf32_round(gy, TF32_EMULATION), tf32_round(x, TF32_EMULATION), tf32_round(w, TF32_EMULATION)
-        gx = torch.nn.grad.conv2d_input(x.shape, wq, gq, padding=ctx.padding)
-        gw = torch.nn.grad.conv2d_weight(xq, w.shape, gq, padding=ctx.padding)
-        return gx, gw, gy.sum(dim=(0, 2, 3)), None
+        g = torch.nn.grad
+        d_in, d_w = (g.conv2d_input, g.conv2d_weight) if x.dim() == 4 else (g.conv3d_input, g.conv3d_weight)
+        gx = d_in(x.shape, wq, gq, stride=ctx.stride, padding=ctx.padding)
+        gw = d_w(xq, w.shape, gq, stride=ctx.stride, padding=ctx.padding)
+        return gx, gw, gy.sum(dim=[0] + list(range(2, gy.dim()))), None, None
 
 
 def conv2d(x, w, b, padding=0):
     if TF32_EMULATION and w.shape[0] in (64, 128, 256) and w.shape[1] in (64, 128, 256):
-        return _Tf32Conv.apply(x, w, b, padding)
+        return _Tf32Conv.apply(x, w, b, padding, 1)
     return F.conv2d(x, w, b, padding=padding)
+
+
+def unet_conv(x, w, b, stride=1, padding=1):
+    """A U-Net convolution (vxm/networks.py:1506-1521).  Under TF32_EMULATION the layers the tcgen05 engine covers
+    (reduction-side channels >= 16: every layer but the 2-channel input layer and the nd-channel flow head, stride 2
+    included - the engine runs those in space-to-depth form on the same operands) use truncated operands."""
+    if TF32_EMULATION and w.shape[0] >= 16 and w.shape[1] >= 16:
+        return _Tf32Conv.apply(x, w, b, padding, stride)
+    conv = F.conv2d if x.dim() == 4 else F.conv3d
+    return conv(x, w, b, stride=stride, padding=padding)
 
 
 def _blur_filt(a, C, scale=1.0):
@@ -188,7 +204,7 @@ def resize_transform(x, vel_resize):
 
 
 def unet(x, sd, n_enc, n_dec, p='unet_model.'):
-    conv = F.conv2d if x.dim() == 4 else F.conv3d
+    conv = unet_conv
     enc = [x]
     for i in range(n_enc):
         enc.append(F.leaky_relu(conv(enc[-1], sd[f'{p}downarm.{i}.main.weight'], sd[f'{p}downarm.{i}.main.bias'], stride=2, padding=1), 0.2))

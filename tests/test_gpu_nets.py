@@ -156,21 +156,29 @@ def test_pad_blur_layers_vs_reference(golden, orc, Fn):
         close(xg.grad.permute(0, 3, 1, 2), xt.grad, 1e-6)
 
 
-@pytest.mark.parametrize("shape", [(8, 12), (4, 6, 8)])
-def test_upsample_concat(shape, Fn):
+@pytest.mark.parametrize("shape,C1,C2,pad_to", [((8, 12), 5, 3, 1), ((4, 6, 8), 5, 3, 1), ((8, 12), 32, 2, 4), ((4, 6, 8), 32, 2, 4),
+                                                 ((6, 4, 10), 64, 32, 4), ((16, 8), 8, 6, 4)])
+def test_upsample_concat(shape, C1, C2, pad_to, Fn):
+    """nearest x2 + concat (vxm networks.py:99-102): scalar kernel and the 128-bit kernels (C1 % 4 == 0, channel stride padded
+    to a multiple of 4: the zero channels the next convolution's TMA loads expect)."""
     nd = len(shape)
-    r = gi.rng(700 + nd)
-    a = torch.from_numpy(r.standard_normal((2, 5, *[s // 2 for s in shape])).astype(np.float32)).requires_grad_()
-    b = torch.from_numpy(r.standard_normal((2, 3, *shape)).astype(np.float32)).requires_grad_()
+    r = gi.rng(700 + nd + C1)
+    a = torch.from_numpy(r.standard_normal((2, C1, *[s // 2 for s in shape])).astype(np.float32)).requires_grad_()
+    b = torch.from_numpy(r.standard_normal((2, C2, *shape)).astype(np.float32)).requires_grad_()
     y = torch.cat([F.interpolate(a, scale_factor=2, mode="nearest"), b], dim=1)
     gy = torch.from_numpy(r.standard_normal(tuple(y.shape)).astype(np.float32))
     y.backward(gy)
     pi, po = (0, *range(2, nd + 2), 1), (0, nd + 1, *range(1, nd + 1))
     ag = a.detach().cuda().permute(*pi).contiguous().requires_grad_()
     bg = b.detach().cuda().permute(*pi).contiguous().requires_grad_()
-    yg = Fn.upsample_concat_cl(ag, bg)
-    assert torch.equal(yg.permute(*po).cpu(), y.detach())
-    yg.backward(gy.cuda().permute(*pi).contiguous())
+    yg = Fn.upsample_concat_cl(ag, bg, pad_channels_to=pad_to)
+    Cs = (C1 + C2 + pad_to - 1) // pad_to * pad_to
+    assert yg.shape[-1] == Cs and float(yg[..., C1 + C2:].abs().sum()) == 0.0
+    assert torch.equal(yg[..., :C1 + C2].permute(*po).cpu(), y.detach())
+    gyp = torch.zeros(yg.shape, device="cuda")
+    gyp[..., :C1 + C2] = gy.cuda().permute(*pi)
+    gyp[..., C1 + C2:] = 7.0                     # gradient of the padding channels must be ignored
+    yg.backward(gyp)
     close(ag.grad.permute(*po), a.grad, 1e-5)
     close(bg.grad.permute(*po), b.grad, 0)
 

@@ -11,19 +11,21 @@ import dfmir_b200.functional as Fn
 S = 256
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 sds = tp.random_state_dicts(ngf=64, n_blocks=9, crop=S, seed=5)
+if os.environ.get('FLOWSCALE', '1') == '1':
+    sds[2]['flow.weight'] = sds[2]['flow.weight'] * 2e4
 A = torch.from_numpy(gi.image_textured(700 + B, B, (S, S)))
 Bm = torch.from_numpy(gi.image_textured(710 + B, B, (S, S)))
 
 
 def ids_for(call):            # 5 layers per NCE call
     sizes = [(S + 6) ** 2, S * S, (S // 2) ** 2, (S // 4) ** 2, (S // 4) ** 2]
-    return [torch.from_numpy(np.random.RandomState(9000 + 100 + call * 5 + i + 1).permutation(n))[:256] for i, n in enumerate(sizes)]
+    return [torch.from_numpy(np.random.RandomState(9000 + 100 + call * 5 + i + 1).permutation(n))[:256].cuda() for i, n in enumerate(sizes)]
 
 
 # ---------------- oracle, float64
-P = {n: {k: v.double().clone().requires_grad_(v.is_floating_point() and not k.endswith(('.filt', '.grid'))) for k, v in sd.items()}
+P = {n: {k: v.double().cuda().clone().requires_grad_(v.is_floating_point() and not k.endswith(('.filt', '.grid'))) for k, v in sd.items()}
      for n, sd in zip('GFR', sds)}
-Ad, Bd = A.double(), Bm.double()
+Ad, Bd = A.double().cuda(), Bm.double().cuda()
 fake = tp.resnet_generator(torch.cat((Ad, Bd), 0), P['G'], 9)
 fake_B, idt_B = fake[:B], fake[B:]
 regA, _, pos_flow = tp.vxm_dense(Ad, Bd, P['R'], 6, 7)
@@ -50,8 +52,8 @@ o_terms = {
 }
 o_g = {}
 for k, t in o_terms.items():
-    gs = torch.autograd.grad(t, [fake, pos_flow, P['G']['model.4.weight']], retain_graph=True, allow_unused=True)
-    o_g[k] = [None if g is None else g.detach() for g in gs]
+    gs = torch.autograd.grad(t, [fake, pos_flow, P['G']['model.4.weight'], regA], retain_graph=True, allow_unused=True)
+    o_g[k] = [None if g is None else g.detach().cpu() for g in gs]
     print("oracle", k, float(t))
 
 # ---------------- ours, under several switches
@@ -65,7 +67,11 @@ def run_ours(tag):
         getattr(m, 'net' + n).load_state_dict(sd, strict=False)
     m.set_input({'A': A, 'B': Bm})
     m.forward()
+    _eng = Fn.CONV_ENGINE
+    if getattr(Fn, "_R_FP32", False):
+        Fn.CONV_ENGINE = "simt"
     y = m.netR(m.real_A, m.real_B)
+    Fn.CONV_ENGINE = _eng
     flow = y[2]
     m.registered = m.spatialTransformer(m.fake_B, flow)
     m.regA = y[0]
@@ -80,9 +86,9 @@ def run_ours(tag):
     terms['smooth'] = rm.smooothing_loss(flow) * 0.2
     w4 = m.netG.model[4].weight
     for k, t in terms.items():
-        gs = torch.autograd.grad(t, [m.fake, flow, w4], retain_graph=True, allow_unused=True)
+        gs = torch.autograd.grad(t, [m.fake, flow, w4, m.regA], retain_graph=True, allow_unused=True)
         line = f"[{tag}] {k:7s} ours {float(t):.6f} oracle {float(o_terms[k]):.6f}"
-        for name, g, ref in zip(("d/dfake", "d/dflow", "d/dw4"), gs, o_g[k]):
+        for name, g, ref in zip(("d/dfake", "d/dflow", "d/dw4", "d/dregA"), gs, o_g[k]):
             if g is None or ref is None:
                 continue
             g = g.detach().cpu().double()
@@ -95,11 +101,12 @@ def run_ours(tag):
 
 
 for tag, setup in [("default", lambda: None),
-                   ("dense_tap_grad", lambda: setattr(Fn, "SPARSE_TAP_GRAD", False)),
                    ("no_stats_epilogue", lambda: setattr(Fn, "STATS_IN_EPILOGUE", False)),
-                   ("no_s2d", lambda: setattr(Fn, "S2D_STRIDED", False)),
-                   ("no_reuse", lambda: setattr(rm, "REUSE_REAL_FEATURES", False)),
+                   ("convs_fp32_only", lambda: setattr(Fn, "UMMA_MIN_POSITIONS", 10 ** 9)),
+                   ("R_fp32", lambda: setattr(Fn, "_R_FP32", True)),
                    ("simt", lambda: setattr(Fn, "CONV_ENGINE", "simt"))]:
     Fn.SPARSE_TAP_GRAD, Fn.STATS_IN_EPILOGUE, Fn.S2D_STRIDED, rm.REUSE_REAL_FEATURES, Fn.CONV_ENGINE = True, True, True, True, "auto"
+    Fn.UMMA_MIN_POSITIONS = 4096
+    Fn._R_FP32 = False
     setup()
     run_ours(tag)
