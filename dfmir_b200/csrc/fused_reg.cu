@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NT)
 fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving, const float* __restrict__ fixed,
                  float* __restrict__ steps, float* __restrict__ flow_full, float* __restrict__ warped,
                  double* __restrict__ partials, float* __restrict__ out, const FusedP p) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   __shared__ double sred[5][NT / 32];
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;

@@ -21,7 +21,7 @@ template <int WIN>
 __global__ void __launch_bounds__(NT)
 ncc_fwd_kernel(const float* __restrict__ I, const float* __restrict__ J, const float* __restrict__ mask,
                double* __restrict__ partials, BoxGeom g, float eps) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   __shared__ double sred[2][NT / 32];
   const long long hw = (long long)g.H * g.W, vol = hw * g.D;
   IJLoader ld{I, J, vol, hw, g.W};
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(NT)
 ncc_bwd_coef_kernel(const float* __restrict__ I, const float* __restrict__ J, const float* __restrict__ mask,
                     const float* __restrict__ fwd_out, const float* __restrict__ grad_loss,
                     float* __restrict__ coef, BoxGeom g, float eps, int reduction) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const long long hw = (long long)g.H * g.W, vol = hw * g.D;
   IJLoader ld{I, J, vol, hw, g.W};
   const float wsz = (float)g.win * (float)g.win * (float)g.wz;
@@ -119,7 +119,7 @@ template <int WIN>
 __global__ void __launch_bounds__(NT)
 ncc_bwd_apply_kernel(const float* __restrict__ I, const float* __restrict__ J, const float* __restrict__ coef,
                      float* __restrict__ dI, BoxGeom g) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const long long hw = (long long)g.H * g.W, vol = hw * g.D;
   CoefLoader ld{coef, vol, hw, (long long)g.B * vol, g.W};
   GradCombine cs{I, J, dI, vol, hw, g.W};

@@ -236,7 +236,9 @@ in_apply_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ stat
                    float4* __restrict__ y, int H, int W, int C4, int relu, int p, int rp, int chunk) {
   const int HP = H + 2 * p, WP = W + 2 * p, RW = W + 2 * rp;
   const int total = HP * WP;
-  const int n = blockIdx.y;
+  // images in descending order: the producing convolution wrote image N - 1 last (those lines are still in L2), and the
+  // consuming convolution starts with image 0, which this kernel then writes last
+  const int n = gridDim.y - 1 - blockIdx.y;
   const int p0 = blockIdx.x * chunk, p1 = min(total, p0 + chunk);
   const int c4 = threadIdx.x % C4, pl = threadIdx.x / C4, npl = 256 / C4;
   if (pl >= npl) return;
@@ -275,7 +277,9 @@ in_bwd_reduce_v4_kernel(const float4* __restrict__ dy, const float4* __restrict_
                         float4* __restrict__ dx, float4* __restrict__ dres, double* __restrict__ sums, int H, int W, int C4,
                         int relu, int p, int rp, int chunk) {
   __shared__ double red[256][8];
-  const int n = blockIdx.y;
+  // descending image order (the tail of the data-gradient convolution's output is still in L2); the apply pass then
+  // runs ascending and starts on the images this kernel wrote last
+  const int n = gridDim.y - 1 - blockIdx.y;
   const int HW = H * W;
   const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
   const int HP = H + 2 * p, WP = W + 2 * p;
