@@ -513,6 +513,309 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
+// ---------------------------------------------------------------- depth-march variant: 3 x 3 x 3, thin layers (BN <= 64)
+// The halo kernel above is bound by the tensor core's shared-memory operand reads, ~74 bytes / clock measured: a
+// 128 x BN x 8 TF32 MMA reads 4 KB of activations however narrow BN is, and a 3 x 3 x 3 layer re-reads every activation
+// row 27 times - 82 clocks per output voxel on the 36 -> 16 channel full-resolution layer of the registration U-Net
+// (7 % of the tensor pipe, 11 % of HBM).  Here a CTA owns a 16 x 8 (h, w) column of voxels and MARCHES along depth:
+// for every INPUT slice u one halo tile {32 ch, 10, 18} is loaded, and each of its nine in-plane taps is multiplied by
+// the weights of all THREE depth taps at once - B = [kd][BN] rows, one MMA of N = 3 * BN - because slice u feeds output
+// slice u + pad - kd through depth tap kd.  The three column groups of that MMA are the accumulators of three
+// consecutive output slices: TMEM is a ring of 512 / BN slots, slot(step) moves down by one per input slice, so an
+// output slice is overwritten by its kd = 0 product, accumulated by kd = 1 and kd = 2 of the next two steps, and then
+// complete: the epilogue drains one slot per step while the MMAs of the following steps run.  Activation reads by the
+// tensor core drop 3x (27 -> 9 per row), the halo tile of a slice is fetched once per column instead of once per
+// SD + 2 slices, and N grows from BN to 3 * BN.
+// tcgen05.mma with the accumulate flag known at compile time (no predicate set-up in the issuing thread, whose
+// instruction rate is what bounds these thin layers: ~7 clocks per instruction for a lone warp)
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+
+// The same two operations issued from CONVERGED code by one elected lane: inside an `if (lane == 0)` region the
+// compiler wraps every uniform-datapath instruction in an ELECT / BRA.U.ANY loop (5 extra instructions per MMA).
+template <bool ACC>
+__device__ __forceinline__ void umma_tf32_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// RES: the whole weight tensor of the layer (<= RES_CHUNKS chunks x 9 in-plane taps x [3][BN] rows) stays in shared memory
+// for the life of the CTA instead of streaming through BST stages once per input slice - on the 36 -> 16 layer the
+// streamed weights were 70 % of the L2 -> shared-memory traffic (108 of 154 KB per slice, 5 TB/s over the chip).
+template <int BN, bool RES = false>
+struct DmCfg {
+  static constexpr int R = 512 / BN;                      // accumulator slots
+  static constexpr int RES_CHUNKS = BN == 16 ? 2 : 1;     // 110.6 KB of weights either way
+  static constexpr int AST = 4;                           // activation stages (one input slice x 32 channels each)
+  static constexpr int BST = BN <= 32 ? 9 : 3;            // weight stages (one in-plane tap x 3 depth taps each); divides 9, so
+                                                          // that the stage of a tap is a compile-time constant
+  static constexpr int NB = 4;                            // steps the epilogue may lag behind the MMA issuer
+  static constexpr int HH = 18, HW = 10;
+  static constexpr int A_ST = (HH * HW * 128 + 1023) / 1024 * 1024;
+  static constexpr int B_ST = 3 * BN * 128;
+  static constexpr int NBARS = 2 * AST + 2 * BST + 2 * NB;
+  static constexpr int B_BYTES = RES ? RES_CHUNKS * 9 * B_ST : BST * B_ST;
+  static constexpr int SMEM = AST * A_ST + B_BYTES + NBARS * 8 + 16 + 1024;
+  static_assert(R >= NB + 4, "the ring must hold the slots in flight");
+  static_assert(!RES || BN <= 32, "resident weights: 16 / 32-channel tiles");
+};
+
+struct DmP {
+  UmmaP u;
+  int zchunk, nzc;         // output slices per work item, items per (h, w) column
+};
+
+template <int BN, bool RES>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_umma_dmarch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const float* __restrict__ bias, float* __restrict__ y, const DmP dp) {
+  using C = DmCfg<BN, RES>;
+  constexpr int R = C::R, AST = C::AST, BST = C::BST, NB = C::NB;
+  const UmmaP& p = dp.u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + AST * C::A_ST;
+  uint64_t* a_full = (uint64_t*)(sB + C::B_BYTES);
+  uint64_t* a_empty = a_full + AST;
+  uint64_t* b_full = a_empty + AST;
+  uint64_t* b_empty = b_full + BST;
+  uint64_t* acc_full = b_empty + BST;
+  uint64_t* acc_empty = acc_full + NB;
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + NB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const int tiles_hw = p.tiles_h * p.tiles_w;
+  const int items = p.N * tiles_hw * dp.nzc * n_tiles;
+  const int cchunks = (p.Cin + KCH - 1) / KCH;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int s = 0; s < AST; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < BST; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> output-channel tile, depth chunk, (h, w) column, image
+  auto decode = [&](int item, int& nt, int& n, int& h0, int& w0, int& z0, int& z1) {
+    nt = item % n_tiles; int rest = item / n_tiles;
+    const int zc = rest % dp.nzc; rest /= dp.nzc;
+    const int tw_i = rest % p.tiles_w; rest /= p.tiles_w;
+    const int th_i = rest % p.tiles_h; n = rest / p.tiles_h;
+    h0 = th_i * 16; w0 = tw_i * 8;
+    z0 = zc * dp.zchunk; z1 = min(p.D, z0 + dp.zchunk);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      uint32_t ia = 0, ib = 0;
+      if constexpr (RES) {          // every weight tile once: stage (cc * 9 + rq), one barrier for all of them
+        mbar_expect_tx(b_full, (uint32_t)(cchunks * 9 * C::B_ST));
+        for (int cc = 0; cc < cchunks; ++cc)
+          for (int tap = 0; tap < 27; ++tap)
+            tma_load_3d(sB + (cc * 9 + tap % 9) * C::B_ST + (tap / 9) * BN * 128, &tmB, b_full, cc * KCH, 0, p.flip ? 26 - tap : tap);
+      }
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int nt, n, h0, w0, z0, z1;
+        decode(item, nt, n, h0, w0, z0, z1);
+        for (int u = z0 - p.pad_d; u <= z1 + 1 - p.pad_d; ++u)
+          for (int cc = 0; cc < cchunks; ++cc, ++ia) {
+            const int sa = ia % AST;
+            mbar_wait(a_empty + sa, ((ia / AST) & 1) ^ 1);
+            mbar_expect_tx(a_full + sa, (uint32_t)(C::HH * C::HW * 128));
+            tma_load_5d(sA + sa * C::A_ST, &tmA, a_full + sa, cc * KCH, w0 - p.pad_w, h0 - p.pad_h, u, n);
+            if constexpr (RES) continue;
+            // tap rq always uses weight stage rq % BST; a stage is used 9 / BST (odd) times per chunk, so the phase of its
+            // j-th use in chunk number ib is (ib + j) & 1
+#pragma unroll
+            for (int rq = 0; rq < 9; ++rq) {
+              const int sb = rq % BST;
+              mbar_wait(b_empty + sb, ((ib + rq / BST) & 1) ^ 1);
+              mbar_expect_tx(b_full + sb, (uint32_t)C::B_ST);
+#pragma unroll
+              for (int kd = 0; kd < 3; ++kd) {
+                const int tap = kd * 9 + rq;
+                tma_load_3d(sB + sb * C::B_ST + kd * BN * 128, &tmB, b_full + sb, cc * KCH, nt * BN, p.flip ? 26 - tap : tap);
+              }
+            }
+            ++ib;
+          }
+      }
+    }
+  } else if (warp == 1) {
+    {
+      // ---------------- MMA issuer: the whole warp walks the loops (converged), one elected lane issues
+      constexpr uint32_t idesc1 = instr_desc_tf32(BM, BN), idesc2 = instr_desc_tf32(BM, 2 * BN), idesc3 = instr_desc_tf32(BM, 3 * BN);
+      constexpr uint64_t GROUP = (uint64_t)(BN * 128 / 16);          // one depth tap's weight rows, in descriptor units
+      const uint64_t bdesc0 = smem_desc_sw128(smem_u32(sB), 16, 1024);
+      // One 32-channel chunk of one input slice: nine in-plane taps, KS K-slices each.  Everything that shapes the
+      // instruction stream is a template argument - KS, whether the three-slot window wraps around the ring (WRAP 1:
+      // slots R-2, R-1 | 0; WRAP 2: R-1 | 0, 1), whether this is the step's first chunk (its very first product
+      // overwrites the newest slot) - so that the issuing thread runs ~7 instructions per tcgen05.mma.
+      auto issue_chunk = [&](auto ks_c, auto wrap_c, auto first_c, uint32_t bph, uint64_t adesc0, int s0, uint64_t bdesc_cc) {
+        constexpr int KS = decltype(ks_c)::value, WRAP = decltype(wrap_c)::value;
+        constexpr bool FIRST = decltype(first_c)::value;
+        const uint32_t c0 = tmem_base + (uint32_t)(s0 * BN);
+        static_for<0, 9>([&](auto rq_c) {
+          constexpr int rq = decltype(rq_c)::value;
+          constexpr int sb = RES ? rq : rq % BST;
+          constexpr int row = (rq / 3) * C::HW + rq % 3;
+          if constexpr (!RES) {
+            mbar_wait(b_full + sb, (bph + rq / BST) & 1);
+            tc_fence_after();
+          }
+          const uint64_t bdesc = bdesc_cc + (uint64_t)(sb * (C::B_ST / 16));
+          const uint64_t adesc = adesc0 + (uint64_t)(8 * row);
+          static_for<0, KS>([&](auto k_c) {
+            constexpr int k = decltype(k_c)::value;
+            const uint64_t ak = adesc + (uint64_t)(2 * k), bk = bdesc + (uint64_t)(2 * k);
+            if constexpr (FIRST && rq == 0 && k == 0) {
+              umma_tf32_elect<false>(c0, ak, bk, idesc1);
+              umma_tf32_elect<true>(tmem_base + (uint32_t)(((s0 + 1) % R) * BN), ak, bk + GROUP, idesc1);
+              umma_tf32_elect<true>(tmem_base + (uint32_t)(((s0 + 2) % R) * BN), ak, bk + 2 * GROUP, idesc1);
+            } else if constexpr (WRAP == 0) {
+              umma_tf32_elect<true>(c0, ak, bk, idesc3);
+            } else if constexpr (WRAP == 1) {
+              umma_tf32_elect<true>(c0, ak, bk, idesc2);
+              umma_tf32_elect<true>(tmem_base, ak, bk + 2 * GROUP, idesc1);
+            } else {
+              umma_tf32_elect<true>(c0, ak, bk, idesc1);
+              umma_tf32_elect<true>(tmem_base, ak, bk + GROUP, idesc2);
+            }
+          });
+          if constexpr (!RES) umma_commit_elect(b_empty + sb);
+        });
+      };
+      auto issue_ks = [&](auto wrap_c, auto first_c, int ksteps, uint32_t bph, uint64_t adesc0, int s0, uint64_t bd) {
+        switch (ksteps) {
+          case 1: issue_chunk(std::integral_constant<int, 1>{}, wrap_c, first_c, bph, adesc0, s0, bd); break;
+          case 2: issue_chunk(std::integral_constant<int, 2>{}, wrap_c, first_c, bph, adesc0, s0, bd); break;
+          case 3: issue_chunk(std::integral_constant<int, 3>{}, wrap_c, first_c, bph, adesc0, s0, bd); break;
+          default: issue_chunk(std::integral_constant<int, 4>{}, wrap_c, first_c, bph, adesc0, s0, bd); break;
+        }
+      };
+      auto issue_wrap = [&](auto first_c, int wrap, int ksteps, uint32_t bph, uint64_t adesc0, int s0, uint64_t bd) {
+        if (wrap == 0) issue_ks(std::integral_constant<int, 0>{}, first_c, ksteps, bph, adesc0, s0, bd);
+        else if (wrap == 1) issue_ks(std::integral_constant<int, 1>{}, first_c, ksteps, bph, adesc0, s0, bd);
+        else issue_ks(std::integral_constant<int, 2>{}, first_c, ksteps, bph, adesc0, s0, bd);
+      };
+      if constexpr (RES) { mbar_wait(b_full, 0); tc_fence_after(); }
+      uint32_t ia = 0, ib = 0, st = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int nt, n, h0, w0, z0, z1;
+        decode(item, nt, n, h0, w0, z0, z1);
+        const int nsteps = z1 - z0 + 2;
+        for (int j = 0; j < nsteps; ++j, ++st) {
+          const uint32_t bi = st % NB;
+          mbar_wait(acc_empty + bi, ((st / NB) & 1) ^ 1);        // the epilogue has drained step st - NB
+          tc_fence_after();
+          const int s0 = (R - (int)(st % R)) % R;                // slot of the output slice first touched by this step
+          const int wrap = s0 + 2 < R ? 0 : (s0 + 2 == R ? 1 : 2);
+          for (int cc = 0; cc < cchunks; ++cc, ++ia, ++ib) {
+            const int sa = ia % AST;
+            mbar_wait(a_full + sa, (ia / AST) & 1);
+            tc_fence_after();
+            const uint64_t adesc0 = smem_desc_sw128(smem_u32(sA + sa * C::A_ST), 16, C::HW * 128);
+            const int rem_c = p.Cin - cc * KCH;
+            const int ksteps = rem_c >= KCH ? KCH / UMMA_K : (rem_c + UMMA_K - 1) / UMMA_K;
+            const uint64_t bd = RES ? bdesc0 + (uint64_t)(cc * 9 * (C::B_ST / 16)) : bdesc0;
+            if (cc == 0) issue_wrap(std::true_type{}, wrap, ksteps, ib & 1, adesc0, s0, bd);
+            else issue_wrap(std::false_type{}, wrap, ksteps, ib & 1, adesc0, s0, bd);
+            umma_commit_elect(a_empty + sa);
+          }
+          umma_commit_elect(acc_full + bi);        // depth tap 2 of this step completed slot s0 + 2
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5 take the even steps, 6..9 the odd ones; one voxel row per thread
+    const int set = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int th = row >> 3, tw = row & 7;
+    const bool vec_ok = p.ys[4] == 1 && (p.Cout & 3) == 0;
+    constexpr int CW = BN < 32 ? BN : 32;
+    uint32_t st = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int nt, n, h0, w0, z0, z1;
+      decode(item, nt, n, h0, w0, z0, z1);
+      const int n0 = nt * BN;
+      const int nsteps = z1 - z0 + 2;
+      const int oh = h0 + th, ow = w0 + tw;
+      const bool inb = oh < p.H && ow < p.W;
+      float* ybase = y + (long long)n * p.ys[0] + (long long)oh * p.ys[2] + (long long)ow * p.ys[3];
+      for (int j = 0; j < nsteps; ++j, ++st) {
+        if ((int)(st & 1) != set) continue;
+        const uint32_t bi = st % NB;
+        mbar_wait(acc_full + bi, (st / NB) & 1);
+        tc_fence_after();
+        if (j >= 2) {
+          const int od = z0 + j - 2;
+          const int slot = ((R - (int)(st % R)) % R + 2) % R;
+          const uint32_t acc = tmem_base + (uint32_t)(slot * BN) + ((uint32_t)(quarter * 32) << 16);
+          float* yp = ybase + (long long)od * p.ys[1];
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += CW) {
+            float v[CW];
+            if (CW == 32) tmem_ld_32x32(acc + (uint32_t)c0, v); else tmem_ld_32x16(acc + (uint32_t)c0, v);
+            if (inb && n0 + c0 < p.Cout) {
+#pragma unroll
+              for (int i = 0; i < CW; ++i) {
+                float t = v[i];
+                if (bias && n0 + c0 + i < p.Cout) t += __ldg(bias + n0 + c0 + i);
+                v[i] = act_apply(t, p.act);
+              }
+              if (vec_ok && n0 + c0 + CW <= p.Cout) {
+                float4* dst = reinterpret_cast<float4*>(yp + n0 + c0);
+#pragma unroll
+                for (int i = 0; i < CW / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < CW; ++i)
+                  if (n0 + c0 + i < p.Cout) yp[(long long)(n0 + c0 + i) * p.ys[4]] = v[i];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + bi);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
 // ---------------------------------------------------------------- CTA-pair variant (cta_group::2), 3x3, 256-channel tiles
 // The single-CTA kernels above are bound by the shared-memory operand reads of the MMA (a TF32 128 x 128 x 8 MMA reads
 // 8 KB for 64 cycles of math, a 128 x 256 x 8 one 12 KB for 128: 59 % / 75 % tensor-pipe activity measured).  Here
@@ -935,6 +1238,63 @@ int launch_pair(const float* act, const Strides5& as, int IH, int IW, const floa
   return DFMIR_OK;
 }
 
+// depth-march kernel: 3-D 3 x 3 x 3, output-channel tiles of 16 / 32 / 64
+template <int BN, bool RES>
+int launch_dmarch(const float* act, const Strides5& as, int ID, int IH, int IW, const float* w, const float* bias, float* y, UmmaP p,
+                  cudaStream_t st, const char* who) {
+  using C = DmCfg<BN, RES>;
+  static_assert(C::SMEM <= 227 * 1024, "shared memory");
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  p.tiles_h = (p.H + 15) / 16; p.tiles_w = (p.W + 7) / 8; p.tiles_d = 1;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const long long cols = (long long)p.N * p.tiles_h * p.tiles_w * n_tiles;
+  // depth chunks per column: fewest slice steps on the critical path, counting the two extra input slices of every
+  // chunk and the rounds of the persistent grid
+  DmP dp;
+  {
+    const long long sms = dfmir_num_sms();
+    long long best = -1; int nzc = 1;
+    for (int c = 1; c <= 32 && p.D / c >= 4; ++c) {
+      const long long rounds = (cols * c + sms - 1) / sms;
+      const long long cost = rounds * ((p.D + c - 1) / c + 2);
+      if (best < 0 || cost < best) { best = cost; nzc = c; }
+    }
+    dp.zchunk = (p.D + nzc - 1) / nzc;
+    dp.nzc = (p.D + dp.zchunk - 1) / dp.zchunk;
+  }
+  p.ptiles = (int)(cols / n_tiles) * dp.nzc;
+  dp.u = p;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p.Cin, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)ID, (cuuint64_t)p.N};
+    cuuint64_t strides[4] = {(cuuint64_t)as.w * 4, (cuuint64_t)as.h * 4, (cuuint64_t)as.d * 4, (cuuint64_t)as.n * 4};
+    cuuint32_t box[5] = {KCH, (cuuint32_t)C::HW, (cuuint32_t)C::HH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(slice tile) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Cout, 27};
+    cuuint64_t strides[2] = {(cuuint64_t)p.Cin * 4, (cuuint64_t)p.Cin * p.Cout * 4};
+    cuuint32_t box[3] = {KCH, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dfmir_set_error("%s: cuTensorMapEncodeTiled(weights) failed (%d)", who, (int)r); return DFMIR_ERR_CUDA; }
+  }
+  DFMIR_CUDA(cudaFuncSetAttribute(conv_umma_dmarch_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+  const long long items = cols * dp.nzc;
+  if (items == 0) return DFMIR_OK;
+  int grid = dfmir_num_sms();
+  if (grid > items) grid = (int)items;
+  const int rounds = (int)((items + grid - 1) / grid);
+  grid = (int)((items + rounds - 1) / rounds);
+  conv_umma_dmarch_kernel<BN, RES><<<grid, THREADS, C::SMEM, st>>>(tmA, tmB, bias, y, dp);
+  DFMIR_CHECK_LAUNCH(who);
+  return DFMIR_OK;
+}
+
 // act: source activation (channels-last, c stride 1) with element strides `as` and spatial size (ID, IH, IW)
 int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const float* w, const float* bias, float* y,
              const UmmaP& p, cudaStream_t st, const char* who, StatArg* stat = nullptr) {
@@ -957,6 +1317,17 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
     if (p.Cout % 256 == 0) return launch_pair<256>(act, as, IH, IW, w, bias, y, p, st, who, stat);
     // DFMIR_UMMA_PAIR=2 also pairs the 128-channel layers: measured slower than the single-CTA 2 x 128 tiles (5.7 vs 5.2 ms / step)
     if (p.Cout % 128 == 0 && pair > 1) return launch_pair<128>(act, as, IH, IW, w, bias, y, p, st, who, stat);
+  }
+  static const int dmarch = getenv("DFMIR_UMMA_DMARCH") ? atoi(getenv("DFMIR_UMMA_DMARCH")) : 1;
+  if (dmarch && ID > 1 && p.KD == 3 && p.KH == 3 && p.KW == 3 && BN <= 64 && !p.per_sample && !p.accum && !stat && p.D >= 8 &&
+      (long long)p.N * p.D * p.H * p.W >= 8192) {
+    static const int res = getenv("DFMIR_UMMA_DMARCH_RES") ? atoi(getenv("DFMIR_UMMA_DMARCH_RES")) : 1;
+    const int cch = (p.Cin + KCH - 1) / KCH;
+    if (BN == 64) return launch_dmarch<64, false>(act, as, ID, IH, IW, w, bias, y, p, st, who);
+    if (BN == 32) return res && cch <= DmCfg<32, true>::RES_CHUNKS ? launch_dmarch<32, true>(act, as, ID, IH, IW, w, bias, y, p, st, who)
+                                                                   : launch_dmarch<32, false>(act, as, ID, IH, IW, w, bias, y, p, st, who);
+    return res && cch <= DmCfg<16, true>::RES_CHUNKS ? launch_dmarch<16, true>(act, as, ID, IH, IW, w, bias, y, p, st, who)
+                                                     : launch_dmarch<16, false>(act, as, ID, IH, IW, w, bias, y, p, st, who);
   }
   CUtensorMap tmA, tmB;
   {

@@ -186,6 +186,13 @@ CASES3D = [  # N, Cin, Cout, D, H, W
     (2, 48, 32, 4, 9, 33),
     (1, 32, 64, 4, 8, 32),           # two output-channel tiles
     (1, 96, 16, 3, 6, 24),
+    # depth-march kernel (csrc/conv_umma.cu: conv_umma_dmarch_kernel; >= 8192 voxels, depth >= 8): 16 / 32 / 64-channel tiles,
+    # 1 - 2 channel chunks, partial (h, w) tiles, several depth chunks, enough steps to wrap the accumulator ring
+    (1, 36, 16, 40, 20, 24),
+    (2, 16, 36, 12, 16, 40),
+    (1, 48, 32, 20, 18, 20),
+    (1, 16, 3, 24, 20, 24),
+    (1, 64, 64, 44, 16, 16),
 ]
 
 
