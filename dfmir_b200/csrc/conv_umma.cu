@@ -538,27 +538,6 @@ __device__ __forceinline__ void umma_tf32_c(uint32_t tmem_d, uint64_t adesc, uin
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
 }
 
-// The same two operations issued from CONVERGED code by one elected lane: inside an `if (lane == 0)` region the
-// compiler wraps every uniform-datapath instruction in an ELECT / BRA.U.ANY loop (5 extra instructions per MMA).
-template <bool ACC>
-__device__ __forceinline__ void umma_tf32_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0) : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // RES: the whole weight tensor of the layer (<= RES_CHUNKS chunks x 9 in-plane taps x [3][BN] rows) stays in shared memory
 // for the life of the CTA instead of streaming through BST stages once per input slice - on the 36 -> 16 layer the
 // streamed weights were 70 % of the L2 -> shared-memory traffic (108 of 154 KB per slice, 5 TB/s over the chip).
