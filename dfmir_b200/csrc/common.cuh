@@ -73,6 +73,31 @@ __device__ __forceinline__ float block_sum(float v, float* smem32) {
   return v;
 }
 
+// Exact unsigned division by a run-time constant without the ~20-instruction integer divide (Granlund & Montgomery):
+// q = n / d for every 32-bit n, d >= 1.  Host side: dfmir_fastdiv(d); device: .div(n), .divmod(n, r).
+struct DfmirFastDiv {
+  uint32_t d, m, s1, s2;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    const uint32_t t = __umulhi(m, n);
+    return (t + ((n - t) >> s1)) >> s2;
+  }
+  __device__ __forceinline__ uint32_t divmod(uint32_t n, uint32_t& r) const {
+    const uint32_t q = div(n);
+    r = n - q * d;
+    return q;
+  }
+};
+static inline DfmirFastDiv dfmir_fastdiv(uint32_t d) {
+  DfmirFastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;                     // ceil(log2 d)
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+  f.s1 = s < 1 ? s : 1;
+  f.s2 = s - f.s1;
+  return f;
+}
+
 // streaming 128-bit load that does not pollute L1 (read-once data)
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;

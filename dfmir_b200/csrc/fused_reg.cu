@@ -41,13 +41,15 @@ struct FusedP {
   int ncc_reduction, grad_penalty;
   float grad_mult;
   int G3[3];                // full-resolution dims right-aligned for the Grad loss (2-D: {1,H,W})
+  DfmirFastDiv dh[3], df[3], dnh, dnf, dg1, dg2;   // exact division by Sh[d], Sf[d], nh, nf, G3[1], G3[2]
 };
 
 // element loops run on 32-bit indices (the host entry rejects volumes with B * nd * nvox >= 2^31)
 template <int ND>
-__device__ __forceinline__ void unravel(int v, const int* S, int* pos) {
+__device__ __forceinline__ void unravel(int v, const DfmirFastDiv* S, int* pos) {
+  uint32_t u = (uint32_t)v;
 #pragma unroll
-  for (int d = ND - 1; d >= 0; --d) { pos[d] = v % S[d]; v /= S[d]; }
+  for (int d = ND - 1; d >= 0; --d) { uint32_t r; u = S[d].divmod(u, r); pos[d] = (int)r; }
 }
 
 template <int ND, int WIN, int CM>
@@ -69,21 +71,39 @@ fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving
     const float* in = k == 0 ? vel : steps + (long long)(k - 1) * slab;
     float* o = steps + (long long)k * slab;
     const float sc = k == 0 ? sc0 : 1.f;
-    for (int it = gtid; it < p.B * nh; it += gthreads) {
-      const int b = it / nh;
-      const int v = it - b * nh;
-      const float* ib = in + (long long)b * ND * p.nh;
-      int pos[ND]; float f[ND];
-      unravel<ND>(v, p.Sh, pos);
+    // two voxels per trip (all gathers of both issued before either result is stored): these phases are bound by
+    // load latency at 16 warps per SM, not by bandwidth
+    for (int it0 = gtid; it0 < p.B * nh; it0 += 2 * gthreads) {
+      float res[2][ND]; long long oo[2]; bool live[2];
 #pragma unroll
-      for (int d = 0; d < ND; ++d) f[d] = ib[(long long)d * p.nh + v] * sc;
-      SampleSite<ND> s;
-      dfmir_make_site<ND, CM>(s, pos, f, p.Sh);
+      for (int u = 0; u < 2; ++u) {
+        const int it = it0 + u * gthreads;
+        live[u] = it < p.B * nh;
+        if (!live[u]) continue;
+        uint32_t vr;
+        const int b = (int)p.dnh.divmod((uint32_t)it, vr);
+        const int v = (int)vr;
+        const float* ib = in + (long long)b * ND * p.nh;
+        int pos[ND]; float f[ND];
+        unravel<ND>(v, p.dh, pos);
 #pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        const float smp = dfmir_sample<ND>(ib + (long long)d * p.nh, s, p.Sh) * sc;
-        o[((long long)b * ND + d) * p.nh + v] = __fadd_rn(f[d], smp);
+        for (int d = 0; d < ND; ++d) f[d] = ib[(long long)d * p.nh + v] * sc;
+        SampleSite<ND> s;
+        dfmir_make_site<ND, CM>(s, pos, f, p.Sh);
+        CornerSet<ND> cs;
+        dfmir_corners<ND>(cs, s, p.Sh);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+          const float smp = dfmir_sample_corners<ND>(ib + (long long)d * p.nh, cs) * sc;
+          res[u][d] = __fadd_rn(f[d], smp);
+        }
+        oo[u] = (long long)b * ND * p.nh + v;
       }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (live[u])
+#pragma unroll
+          for (int d = 0; d < ND; ++d) o[oo[u] + (long long)d * p.nh] = res[u][d];
     }
     grid.sync();
   }
@@ -91,20 +111,39 @@ fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving
   // ---- phase nsteps+1: upsample the integrated field and warp the moving image
   {
     const float* field = steps + (long long)(p.nsteps - 1) * slab;
-    for (int it = gtid; it < p.B * nf; it += gthreads) {
-      const int b = it / nf;
-      const int v = it - b * nf;
-      int pos[ND]; float f[ND];
-      unravel<ND>(v, p.Sf, pos);
+    // (single-channel images take the two-voxel path; more channels keep one voxel per trip)
+    for (int it0 = gtid; it0 < p.B * nf; it0 += 2 * gthreads) {
+      float f[2][ND], wv[2]; int bb[2], vv[2]; bool live[2];
+      CornerSet<ND> cs[2];
 #pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        f[d] = resizedev::interp<ND, int>(field + ((long long)b * ND + d) * p.nh, p.rg, v, p.pre_mul);   // post_mul = 1
-        flow_full[((long long)b * ND + d) * p.nf + v] = f[d];
+      for (int u = 0; u < 2; ++u) {
+        const int it = it0 + u * gthreads;
+        live[u] = it < p.B * nf;
+        if (!live[u]) continue;
+        uint32_t vr;
+        bb[u] = (int)p.dnf.divmod((uint32_t)it, vr);
+        vv[u] = (int)vr;
+        int pos[ND];
+        unravel<ND>(vv[u], p.df, pos);
+        int i0[ND], i1[ND]; float l0[ND], l1[ND];
+        resizedev::setup_pos<ND>(p.rg, pos, i0, i1, l0, l1);        // one interpolation site for the nd components
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          f[u][d] = resizedev::interp_site<ND>(field + ((long long)bb[u] * ND + d) * p.nh, p.rg, i0, i1, l0, l1, p.pre_mul);   // post_mul = 1
+        SampleSite<ND> s;
+        dfmir_make_site<ND, CM>(s, pos, f[u], p.Sf);
+        dfmir_corners<ND>(cs[u], s, p.Sf);
+        wv[u] = dfmir_sample_corners<ND>(moving + (long long)bb[u] * p.C * p.nf, cs[u]);
       }
-      SampleSite<ND> s;
-      dfmir_make_site<ND, CM>(s, pos, f, p.Sf);
-      for (int c = 0; c < p.C; ++c)
-        warped[((long long)b * p.C + c) * p.nf + v] = dfmir_sample<ND>(moving + ((long long)b * p.C + c) * p.nf, s, p.Sf);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!live[u]) continue;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) flow_full[((long long)bb[u] * ND + d) * p.nf + vv[u]] = f[u][d];
+        warped[(long long)bb[u] * p.C * p.nf + vv[u]] = wv[u];
+        for (int c = 1; c < p.C; ++c)
+          warped[((long long)bb[u] * p.C + c) * p.nf + vv[u]] = dfmir_sample_corners<ND>(moving + ((long long)bb[u] * p.C + c) * p.nf, cs[u]);
+      }
     }
     grid.sync();
   }
@@ -123,15 +162,42 @@ fused_reg_kernel(const float* __restrict__ vel, const float* __restrict__ moving
   {
     const int st1 = p.G3[2], st0 = p.G3[1] * p.G3[2];
     const int total = p.B * ND * nf;
-    for (int it = gtid; it < total; it += gthreads) {
-      const int v = it % nf;
-      const int px = v % p.G3[2];
-      const int py = (v / p.G3[2]) % p.G3[1];
-      const int pz = v / st0;
-      const float c = flow_full[it];
-      if (px + 1 < p.G3[2]) { float d = fabsf(flow_full[it + 1] - c); acc[2] += p.grad_penalty == 2 ? d * d : d; }
-      if (py + 1 < p.G3[1]) { float d = fabsf(flow_full[it + st1] - c); acc[1] += p.grad_penalty == 2 ? d * d : d; }
-      if (pz + 1 < p.G3[0]) { float d = fabsf(flow_full[it + st0] - c); acc[0] += p.grad_penalty == 2 ? d * d : d; }
+    auto pen = [&](float a, float c) { const float d = fabsf(a - c); return p.grad_penalty == 2 ? d * d : d; };
+    if ((st1 & 3) == 0) {
+      // four voxels along x per thread: the centre, the y + 1 and z + 1 rows as 128-bit loads (rows are 16-byte
+      // aligned: W % 4 == 0), one scalar for the x neighbour of the fourth voxel
+      const float4* f4 = reinterpret_cast<const float4*>(flow_full);
+      for (int i4 = gtid; i4 < total / 4; i4 += gthreads) {
+        const int it = 4 * i4;
+        uint32_t vr, pxr, pyr;
+        p.dnf.divmod((uint32_t)it, vr);
+        const uint32_t row = p.dg2.divmod(vr, pxr);
+        const int pz = (int)p.dg1.divmod(row, pyr);
+        const int px = (int)pxr, py = (int)pyr;
+        const bool hy = py + 1 < p.G3[1], hz = pz + 1 < p.G3[0], hx = px + 4 < p.G3[2];
+        const float4 c = f4[i4];
+        float4 ny = c, nz = c;
+        float nx = c.w;
+        if (hy) ny = f4[i4 + st1 / 4];
+        if (hz) nz = f4[i4 + st0 / 4];
+        if (hx) nx = flow_full[it + 4];
+        acc[2] += pen(c.y, c.x); acc[2] += pen(c.z, c.y); acc[2] += pen(c.w, c.z);
+        if (hx) acc[2] += pen(nx, c.w);
+        if (hy) { acc[1] += pen(ny.x, c.x); acc[1] += pen(ny.y, c.y); acc[1] += pen(ny.z, c.z); acc[1] += pen(ny.w, c.w); }
+        if (hz) { acc[0] += pen(nz.x, c.x); acc[0] += pen(nz.y, c.y); acc[0] += pen(nz.z, c.z); acc[0] += pen(nz.w, c.w); }
+      }
+    } else {
+      for (int it = gtid; it < total; it += gthreads) {
+        uint32_t vr, pxr, pyr;
+        p.dnf.divmod((uint32_t)it, vr);
+        const uint32_t row = p.dg2.divmod(vr, pxr);
+        const int pz = (int)p.dg1.divmod(row, pyr);
+        const int px = (int)pxr, py = (int)pyr;
+        const float c = flow_full[it];
+        if (px + 1 < p.G3[2]) acc[2] += pen(flow_full[it + 1], c);
+        if (py + 1 < p.G3[1]) acc[1] += pen(flow_full[it + st1], c);
+        if (pz + 1 < p.G3[0]) acc[0] += pen(flow_full[it + st0], c);
+      }
     }
   }
   {
@@ -241,11 +307,14 @@ extern "C" int dfmir_fused_reg_fwd(const float* vel, const float* moving, const 
     p.rg.sc[d] = p.rg.O[d] > 1 ? (float)(p.rg.I[d] - 1) / (float)(p.rg.O[d] - 1) : 0.f;
   }
   p.pre_mul = 2.0f;
+  for (int d = 0; d < 3; ++d) { p.dh[d] = dfmir_fastdiv((uint32_t)p.Sh[d]); p.df[d] = dfmir_fastdiv((uint32_t)p.Sf[d]); }
+  p.dnh = dfmir_fastdiv((uint32_t)p.nh); p.dnf = dfmir_fastdiv((uint32_t)p.nf);
   DFMIR_CHECK_ARG(make_box(p.box, B, nd, full_shape, win) == 0, "%s: bad NCC geometry", who);
   const dim3 bg = box_grid(p.box);
   p.tiles_x = bg.x; p.tiles_y = bg.y; p.tiles_z = bg.z;
   p.eps = eps; p.ncc_reduction = ncc_reduction; p.grad_penalty = grad_penalty; p.grad_mult = grad_mult;
   for (int d = 0; d < 3; ++d) { const int src = d - (3 - nd); p.G3[d] = src >= 0 ? full_shape[src] : 1; }
+  p.dg1 = dfmir_fastdiv((uint32_t)p.G3[1]); p.dg2 = dfmir_fastdiv((uint32_t)p.G3[2]);
   cudaStream_t st = (cudaStream_t)stream;
   double* partials = (double*)ws;
 #define FUSED_CASE(NDv, WINv)                                                                                        \

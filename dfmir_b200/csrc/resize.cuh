@@ -29,11 +29,25 @@ __device__ __forceinline__ void setup(const RGeom& g, I v, int* i0, int* i1, flo
 }
 
 
-// value of output voxel v of one plane: pre_mul is applied to every input sample (layers.py:91-94)
-template <int ND, typename I>
-__device__ __forceinline__ float interp(const float* __restrict__ xp, const RGeom& g, I v, float pre_mul) {
-  int i0[ND], i1[ND]; float l0[ND], l1[ND];
-  setup<ND, I>(g, v, i0, i1, l0, l1);
+// the same from the output position itself (callers that already hold it: no division)
+template <int ND>
+__device__ __forceinline__ void setup_pos(const RGeom& g, const int* pos, int* i0, int* i1, float* l0, float* l1) {
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const float s = g.sc[d] * (float)pos[d];
+    int a = (int)s;
+    if (a > g.I[d] - 1) a = g.I[d] - 1;
+    i0[d] = a;
+    i1[d] = a + (a < g.I[d] - 1 ? 1 : 0);
+    l1[d] = s - (float)a;
+    l0[d] = 1.0f - l1[d];
+  }
+}
+
+// value of one plane at a prepared site: pre_mul is applied to every input sample (layers.py:91-94)
+template <int ND>
+__device__ __forceinline__ float interp_site(const float* __restrict__ xp, const RGeom& g, const int* i0, const int* i1,
+                                             const float* l0, const float* l1, float pre_mul) {
   float r;
   if (ND == 1) {
     r = l0[0] * (pre_mul * xp[i0[0]]) + l1[0] * (pre_mul * xp[i1[0]]);
@@ -52,6 +66,14 @@ __device__ __forceinline__ float interp(const float* __restrict__ xp, const RGeo
                  l1[1] * (l0[2] * (pre_mul * xp[z1 + y1 + a]) + l1[2] * (pre_mul * xp[z1 + y1 + b])));
   }
   return r;
+}
+
+// value of output voxel v of one plane
+template <int ND, typename I>
+__device__ __forceinline__ float interp(const float* __restrict__ xp, const RGeom& g, I v, float pre_mul) {
+  int i0[ND], i1[ND]; float l0[ND], l1[ND];
+  setup<ND, I>(g, v, i0, i1, l0, l1);
+  return interp_site<ND>(xp, g, i0, i1, l0, l1, pre_mul);
 }
 
 }  // namespace resizedev

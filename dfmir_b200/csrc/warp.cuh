@@ -98,3 +98,38 @@ __device__ __forceinline__ float dfmir_sample(const float* __restrict__ plane, c
   }
   return acc;
 }
+
+// The same gather with the corner offsets / weights / bounds computed ONCE per site and shared by every plane
+// sampled there (the nd components of a field, the channels of an image): same products, same order of additions
+// as dfmir_sample, so results are bit-identical.  Offsets are plane-relative and fit 32 bits for < 2^31 voxels.
+template <int ND>
+struct CornerSet {
+  int off[1 << ND];
+  float w[1 << ND];
+  bool ok[1 << ND];
+};
+
+template <int ND>
+__device__ __forceinline__ void dfmir_corners(CornerSet<ND>& cs, const SampleSite<ND>& s, const int* S) {
+#pragma unroll
+  for (int c = 0; c < (1 << ND); ++c) {
+    int off = 0;
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      const int id = s.i0[d] + ((c >> (ND - 1 - d)) & 1);
+      ok = ok && (id >= 0) && (id < S[d]);
+      off = off * S[d] + id;
+    }
+    cs.off[c] = off; cs.ok[c] = ok; cs.w[c] = dfmir_corner_weight<ND>(s, c);
+  }
+}
+
+template <int ND>
+__device__ __forceinline__ float dfmir_sample_corners(const float* __restrict__ plane, const CornerSet<ND>& cs) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < (1 << ND); ++c)
+    if (cs.ok[c]) acc += __ldg(plane + cs.off[c]) * cs.w[c];
+  return acc;
+}
