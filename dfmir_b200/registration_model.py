@@ -50,6 +50,8 @@ def default_options(**overrides):
 # feat_k of real_A / real_B taken from the full generator pass instead of three extra encoder passes
 # (identical values; DFMIR_REUSE_REAL_FEATURES=0 restores the reference's schedule pass for pass)
 REUSE_REAL_FEATURES = os.environ.get("DFMIR_REUSE_REAL_FEATURES", "1") != "0"
+# the three optimizers as csrc/adam.cu launches (DFMIR_FUSED_ADAM=0: torch.optim.Adam, capturable in graph mode)
+FUSED_ADAM = os.environ.get("DFMIR_FUSED_ADAM", "1") != "0"
 
 _test_image_cache = {}
 
@@ -342,6 +344,9 @@ class REGISTRATIONModel(BaseModel):
         captured step keeps following the schedulers, which fill the tensor in place."""
         cap = bool(getattr(self.opt, 'cuda_graph', False))
         lr = torch.tensor(float(self.opt.lr), dtype=torch.float32, device=self.device) if cap else self.opt.lr
+        if FUSED_ADAM:       # csrc/adam.cu: one launch per optimizer (torch's capturable Adam: ~6 multi-tensor launches)
+            from .optim import FusedAdam
+            return FusedAdam(params, lr=lr, betas=(self.opt.beta1, self.opt.beta2))
         return torch.optim.Adam(params, lr=lr, betas=(self.opt.beta1, self.opt.beta2), capturable=cap)
 
     def data_dependent_initialize(self, data):

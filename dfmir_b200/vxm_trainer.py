@@ -25,7 +25,11 @@ class VxmRegistrationTrainer:
         self.cuda_graph = bool(cuda_graph)
         lr_ = torch.tensor(float(lr), dtype=torch.float32, device=self.device) if self.cuda_graph else lr
         self.params = [p for p in self.netR.parameters() if p.requires_grad]
-        self.optimizer = torch.optim.Adam(self.params, lr=lr_, betas=betas, capturable=self.cuda_graph)
+        if os.environ.get("DFMIR_FUSED_ADAM", "1") != "0":
+            from .optim import FusedAdam
+            self.optimizer = FusedAdam(self.params, lr=lr_, betas=betas)        # csrc/adam.cu: one launch
+        else:
+            self.optimizer = torch.optim.Adam(self.params, lr=lr_, betas=betas, capturable=self.cuda_graph)
         self.loss_names = ['ncc', 'grad']
         self.loss_ncc = self.loss_grad = None
         self._flat_grad, self._world, self._graph = None, 1, None

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DFMIR_ABI_VERSION 6
+#define DFMIR_ABI_VERSION 7
 
 #define DFMIR_INTERP_LINEAR 0
 #define DFMIR_INTERP_NEAREST 1
@@ -239,6 +239,16 @@ int dfmir_l2norm_bwd(const float* x, const float* norms, const float* dy, float*
 int dfmir_gemm(const float* A, const float* B, const float* bias, float* C, int batch, int M, int N, int K,
                const long long* sA, const long long* sB, const long long* sC, float alpha, int accumulate, int relu,
                void* stream);
+
+/* ---- fused multi-tensor Adam — torch.optim.Adam of models/registration_model.py:114-115,135 (optimizer_G / _F / _R:
+ * lr opt.lr, betas (opt.beta1, opt.beta2), eps 1e-8) stepped at :168-171.  One launch per optimizer.
+ * tensors: device array of 40-byte records {float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+ * int64 numel}; work: device array of n_work int pairs {tensor, chunk} (chunks of dfmir_adam_chunk_elems() elements);
+ * step: device float, incremented before the update; lr_dev: device float, or NULL to use lr_host.  Hyper-parameters
+ * are doubles: the step's scalars (1 - beta, bias corrections) are formed in double like torch.optim.Adam's. */
+int dfmir_adam_chunk_elems(void);
+int dfmir_adam_multi(const void* tensors, const void* work, int n_work, float* step, const float* lr_dev, double lr_host,
+                     double beta1, double beta2, double eps, void* stream);
 
 #ifdef __cplusplus
 }
