@@ -110,3 +110,17 @@ def test_no_grad_forward_after_replay_uses_current_weights():
     Fn._pack_cache.clear(); umma._kmajor_cache.clear()
     model.test()
     assert torch.equal(got, model.fake_B), "a no-grad forward after graph replays ran on stale weight copies"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2); recorded run: profiles/r2_ddp_equiv.txt")
+def test_two_ranks_equal_one_rank_with_the_whole_batch():
+    """2 ranks x batch 2 == 1 rank x batch 4 (losses, averaged gradients, parameters after Adam): tools/check_ddp_equiv.py
+    under torchrun (reference: nn.DataParallel splits one batch, models/base_model.py:103-107)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "check_ddp_equiv.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "EQUAL" in r.stdout
