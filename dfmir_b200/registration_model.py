@@ -52,6 +52,8 @@ def default_options(**overrides):
 REUSE_REAL_FEATURES = os.environ.get("DFMIR_REUSE_REAL_FEATURES", "1") != "0"
 # the three optimizers as csrc/adam.cu launches (DFMIR_FUSED_ADAM=0: torch.optim.Adam, capturable in graph mode)
 FUSED_ADAM = os.environ.get("DFMIR_FUSED_ADAM", "1") != "0"
+# the three PatchNCE terms of a step through netF / the loss kernels in one batch (DFMIR_BATCH_NCE=0: one call per term)
+BATCH_NCE_TERMS = os.environ.get("DFMIR_BATCH_NCE", "1") != "0"
 
 _test_image_cache = {}
 
@@ -428,9 +430,19 @@ class REGISTRATIONModel(BaseModel):
                                                if pos_flow.shape[0] > 1 else test_image, pos_flow)
         self._zero_grads()
 
-        self.loss_G = self.compute_G_loss()
+        if (BATCH_NCE_TERMS and self.opt.lambda_NCE > 0.0 and self.opt.nce_idt and self.netF.use_mlp and self.netF.mlp_init
+                and not self.opt.flip_equivariance and not self.opt.nce_includes_all_negatives_from_minibatch):
+            # the three PatchNCE terms of the step (:152-158, :218-226) share netF: their sampled rows go through its MLPs
+            # and the loss kernels together (same values per row, a third of the launches)
+            self.loss_NCE, self.loss_NCE_Y, local = self._nce_losses_batched(
+                [(self.real_A, self.fake_B), (self.real_B, self.idt_B), (self.real_B, self.regA)])
+            self.loss_G_GAN = 0.0
+            self.loss_G = self.loss_G_GAN + (self.loss_NCE + self.loss_NCE_Y) * 0.5
+            self.loss_local = local * 0.25
+        else:
+            self.loss_G = self.compute_G_loss()
+            self.loss_local = self.calculate_NCE_loss(self.real_B, self.regA) * 0.25
         # masked L1 terms: mask = (u > -0.95) | (v > -0.95) built inside the loss kernel (:160-161)
-        self.loss_local = self.calculate_NCE_loss(self.real_B, self.regA) * 0.25
         l1_a, l1_b = self._masked_l1_pair((self.registered, self.real_B, self.real_B, self.registered),
                                           (self.idt_B, self.registered, self.idt_B, self.registered))
         self.loss_R = l1_a * 1.0 + l1_b * 1.0 + self.loss_local * 1.0
@@ -520,6 +532,52 @@ class REGISTRATIONModel(BaseModel):
             loss = crit(f_q, f_k) * self.opt.lambda_NCE
             total_nce_loss += loss.mean()
         return total_nce_loss / n_layers
+
+    def _nce_losses_batched(self, pairs):
+        """calculate_NCE_loss for several (src, tgt) pairs at once.  Patch ids are drawn in the reference's order (pair by
+        pair, layer by layer); per layer the sampled rows of all pairs are concatenated, so that each MLP of netF and the
+        PatchNCE kernels run once on len(pairs) * B images (negatives stay per image: the batch count of the loss kernel
+        is len(pairs) * B).  Every row sees exactly the arithmetic of the one-pair path."""
+        from . import functional as Fn
+        n_layers, T = len(self.nce_layers), len(pairs)
+        B = self.real_A.size(0)
+        P = self.opt.num_patches
+        feats_q = [self.netG(tgt, self.nce_layers, encode_only=True) for _, tgt in pairs]
+        feats_k = []
+        with torch.no_grad():
+            for src, _ in pairs:
+                if self._real_feats is not None and src is self.real_A:
+                    feats_k.append([f[:B] for f in self._real_feats])
+                elif self._real_feats is not None and src is self.real_B:
+                    feats_k.append([f[B:] for f in self._real_feats])
+                else:
+                    feats_k.append(self.netG(src, self.nce_layers, encode_only=True))
+        ids = []
+        for t in range(T):
+            row = []
+            for feat in feats_k[t]:
+                hw = feat.shape[2] * feat.shape[3]
+                pid = torch.randperm(hw, device=feat.device, generator=self.netF.generator) if self.netF.generator is not None \
+                    else torch.randperm(hw, device=feat.device)
+                row.append(pid[:int(min(P, pid.shape[0]))])
+            ids.append(row)
+        self._last_patch_ids = ids[-1]
+        batch = T * B
+        totals = [0.0] * T
+        for li in range(n_layers):
+            mlp = getattr(self.netF, 'mlp_%d' % li)
+
+            def project(rows):
+                rows = Fn.linear(rows, mlp[0].weight, mlp[0].bias, relu=True)
+                return Fn.l2norm_rows(Fn.linear(rows, mlp[2].weight, mlp[2].bias))
+            with torch.no_grad():
+                k_pool = project(torch.cat([Fn.gather_patches(feats_k[t][li], ids[t][li]) for t in range(T)], 0))
+            q_pool = project(torch.cat([Fn.gather_patches(feats_q[t][li], ids[t][li]) for t in range(T)], 0))
+            per_row = Fn.patchnce(q_pool, k_pool, batch, self.opt.nce_T) * self.opt.lambda_NCE
+            n = per_row.shape[0] // T
+            for t in range(T):
+                totals[t] = totals[t] + per_row[t * n:(t + 1) * n].mean()
+        return [x / n_layers for x in totals]
 
     def calculate_L1_loss(self, src, tgt, mask):
         return losses.calculate_L1_loss(src, tgt, mask)
