@@ -391,16 +391,24 @@ conv_wgrad_fewco_kernel(const float* __restrict__ x, const float* __restrict__ d
 }
 
 // dx = dy * act'(y) on contiguous arrays (LeakyReLU(0.2) / tanh / ReLU of a conv epilogue)
+__device__ __forceinline__ float act_grad(float yv, float g, int act) {
+  if (act == DFMIR_ACT_LEAKY) return yv > 0.f ? g : 0.2f * g;
+  if (act == DFMIR_ACT_TANH) return g * (1.f - yv * yv);
+  if (act == DFMIR_ACT_RELU) return yv > 0.f ? g : 0.f;
+  return g;
+}
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, long long n,
                int act) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float yv = y[i], g = dy[i];
-    float r = g;
-    if (act == DFMIR_ACT_LEAKY) r = yv > 0.f ? g : 0.2f * g;
-    else if (act == DFMIR_ACT_TANH) r = g * (1.f - yv * yv);
-    else if (act == DFMIR_ACT_RELU) r = yv > 0.f ? g : 0.f;
-    dx[i] = r;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = act_grad(y[i], dy[i], act);
+}
+// 128-bit variant (16-byte aligned arrays): n4 float4 elements
+__global__ void __launch_bounds__(256)
+act_bwd_v4_kernel(const float4* __restrict__ y, const float4* __restrict__ dy, float4* __restrict__ dx, long long n4, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = y[i], g = dy[i];
+    dx[i] = make_float4(act_grad(a.x, g.x, act), act_grad(a.y, g.y, act), act_grad(a.z, g.z, act), act_grad(a.w, g.w, act));
   }
 }
 
@@ -545,9 +553,14 @@ extern "C" int dfmir_act_bwd(const float* y, const float* dy, float* dx, long lo
   DFMIR_CHECK_ARG(y && dy && dx && n >= 0, "dfmir_act_bwd: null pointer / bad n");
   DFMIR_CHECK_ARG(act >= DFMIR_ACT_NONE && act <= DFMIR_ACT_RELU, "dfmir_act_bwd: unknown activation %d", act);
   if (n == 0) return DFMIR_OK;
-  long long blocks = (n + 255) / 256;
   const long long cap = (long long)dfmir_num_sms() * 16;
-  act_bwd_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n, act);
+  if ((n & 3) == 0 && ((((uintptr_t)y) | ((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0) {
+    const long long blocks = (n / 4 + 255) / 256;
+    act_bwd_v4_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>((const float4*)y, (const float4*)dy, (float4*)dx, n / 4, act);
+  } else {
+    const long long blocks = (n + 255) / 256;
+    act_bwd_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, n, act);
+  }
   DFMIR_CHECK_LAUNCH("dfmir_act_bwd");
   return DFMIR_OK;
 }

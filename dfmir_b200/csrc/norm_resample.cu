@@ -13,6 +13,23 @@
 
 namespace {
 
+// i -> (i0, i1, i2, i3) for extents (d0, d1, d2, *), i0 fastest.  32-bit divisions when the element count allows: a 64-bit
+// divide by a run-time divisor costs ~100 instructions, and these kernels move only 4 - 16 bytes per thread.
+__device__ __forceinline__ void unravel4(long long i, bool small, int d0, int d1, int d2, int& i0, int& i1, int& i2, int& i3) {
+  if (small) {
+    unsigned q = (unsigned)i, t;
+    t = q / (unsigned)d0; i0 = (int)(q - t * (unsigned)d0); q = t;
+    t = q / (unsigned)d1; i1 = (int)(q - t * (unsigned)d1); q = t;
+    t = q / (unsigned)d2; i2 = (int)(q - t * (unsigned)d2); i3 = (int)t;
+  } else {
+    long long q = i;
+    i0 = (int)(q % d0); q /= d0;
+    i1 = (int)(q % d1); q /= d1;
+    i2 = (int)(q % d2); i3 = (int)(q / d2);
+  }
+}
+
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {  // ReflectionPad: no edge repeat
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
@@ -106,11 +123,8 @@ in_apply_kernel(const float* __restrict__ x, const float* __restrict__ stats, co
   const int HP = H + 2 * p, WP = W + 2 * p;
   const long long total = (long long)N * HP * WP * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int c = (int)(q % C); q /= C;
-    const int wp = (int)(q % WP); q /= WP;
-    const int hp = (int)(q % HP); q /= HP;
-    const int n = (int)q;
+    int c, wp, hp, n;
+    unravel4(i, total < (1LL << 32), C, WP, HP, c, wp, hp, n);
     const int h = reflect_idx(hp - p, H), w = reflect_idx(wp - p, W);
     const float mean = __ldg(stats + ((long long)n * C + c) * 2), rstd = __ldg(stats + ((long long)n * C + c) * 2 + 1);
     float v = (x[(((long long)n * H + h) * W + w) * C + c] - mean) * rstd;
@@ -451,11 +465,8 @@ pad_reflect_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N
   const int HP = H + 2 * p, WP = W + 2 * p;
   const long long total = (long long)N * HP * WP * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int c = (int)(q % C); q /= C;
-    const int wp = (int)(q % WP); q /= WP;
-    const int hp = (int)(q % HP); q /= HP;
-    const int n = (int)q;
+    int c, wp, hp, n;
+    unravel4(i, total < (1LL << 32), C, WP, HP, c, wp, hp, n);
     y[i] = x[(((long long)n * H + reflect_idx(hp - p, H)) * W + reflect_idx(wp - p, W)) * C + c];
   }
 }
@@ -465,11 +476,8 @@ pad_reflect_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int
   const int HP = H + 2 * p, WP = W + 2 * p;
   const long long total = (long long)N * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int c = (int)(q % C); q /= C;
-    const int w = (int)(q % W); q /= W;
-    const int h = (int)(q % H); q /= H;
-    const int n = (int)q;
+    int c, w, h, n;
+    unravel4(i, total < (1LL << 32), C, W, H, c, w, h, n);
     int hl[3], wl[3];
     const int nh = fold_list(h, H, p, hl), nw = fold_list(w, W, p, wl);
     float g = 0.f;
@@ -496,11 +504,8 @@ __global__ void __launch_bounds__(256)
 blur_down_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW) {
   const long long total = (long long)N * OH * OW * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int c = (int)(q % C); q /= C;
-    const int ow = (int)(q % OW); q /= OW;
-    const int oh = (int)(q % OH); q /= OH;
-    const int n = (int)q;
+    int c, ow, oh, n;
+    unravel4(i, total < (1LL << 32), C, OW, OH, c, ow, oh, n);
     const T* xb = x + (long long)n * H * W * C + c;
     T acc = vzero(T());
 #pragma unroll
@@ -539,11 +544,8 @@ __global__ void __launch_bounds__(256)
 blur_down_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
   const long long total = (long long)N * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int c = (int)(q % C); q /= C;
-    const int w = (int)(q % W); q /= W;
-    const int h = (int)(q % H); q /= H;
-    const int n = (int)q;
+    int c, w, h, n;
+    unravel4(i, total < (1LL << 32), C, W, H, c, w, h, n);
     const Adj3 ah = blur_down_adj(h, H, OH), aw = blur_down_adj(w, W, OW);
     const T* gb = dy + (long long)n * OH * OW * C + c;
     T acc = vzero(T());
@@ -565,11 +567,8 @@ blur_up_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int
   const int OH = 2 * H, OW = 2 * W;
   const long long total = (long long)N * OH * OW * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int c = (int)(q % C); q /= C;
-    const int ow = (int)(q % OW); q /= OW;
-    const int oh = (int)(q % OH); q /= OH;
-    const int n = (int)q;
+    int c, ow, oh, n;
+    unravel4(i, total < (1LL << 32), C, OW, OH, c, ow, oh, n);
     const int mh = oh >> 1, mw = ow >> 1;
     const int h0 = (oh & 1) ? mh : max(mh - 1, 0), h1 = (oh & 1) ? min(mh + 1, H - 1) : mh;
     const int w0 = (ow & 1) ? mw : max(mw - 1, 0), w1 = (ow & 1) ? min(mw + 1, W - 1) : mw;
@@ -604,11 +603,8 @@ blur_up_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, i
   const int OW = 2 * W, OH = 2 * H;
   const long long total = (long long)N * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int c = (int)(q % C); q /= C;
-    const int w = (int)(q % W); q /= W;
-    const int h = (int)(q % H); q /= H;
-    const int n = (int)q;
+    int c, w, h, n;
+    unravel4(i, total < (1LL << 32), C, W, H, c, w, h, n);
     const Adj4 ah = blur_up_adj(h, H), aw = blur_up_adj(w, W);
     const T* gb = dy + (long long)n * OH * OW * C + c;
     T acc = vzero(T());
@@ -652,26 +648,26 @@ upcat_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float
 // 128-bit variant (C1 % 4 == 0, Cs % 4 == 0): one float4 of one output voxel per thread.  The first C1 / 4 quads are
 // copies of the parent voxel's quads; the remaining ones are assembled from the skip tensor (whole quads when C2 % 4 == 0)
 // and the zero padding.
+template <typename IDX>      // unsigned when the element count fits 32 bits (64-bit divides dominated this copy kernel)
 __global__ void __launch_bounds__(256)
 upcat_fwd_v4_kernel(const float4* __restrict__ a, const float* __restrict__ b, float4* __restrict__ y, UcGeom g) {
   const int Q = g.Cs >> 2, Q1 = g.C1 >> 2;
-  const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
-  const long long total = (long long)g.N * vox * Q;
+  const long long total = (long long)g.N * g.S[0] * g.S[1] * g.S[2] * Q;
   const int L0 = g.S[0] > 1 ? g.S[0] / 2 : 1, L1 = g.S[1] / 2, L2 = g.S[2] / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / Q;
-    const int j = (int)(i - pix * Q);
+    const IDX pix = (IDX)i / (IDX)Q;
+    const int j = (int)((IDX)i - pix * (IDX)Q);
     float4 v;
     if (j < Q1) {
-      long long q = pix;
-      const int xw = (int)(q % g.S[2]); q /= g.S[2];
-      const int yh = (int)(q % g.S[1]); q /= g.S[1];
-      const int zd = (int)(q % g.S[0]); q /= g.S[0];
+      IDX q = pix;
+      const int xw = (int)(q % (IDX)g.S[2]); q /= (IDX)g.S[2];
+      const int yh = (int)(q % (IDX)g.S[1]); q /= (IDX)g.S[1];
+      const int zd = (int)(q % (IDX)g.S[0]); q /= (IDX)g.S[0];
       const int lz = g.S[0] > 1 ? zd >> 1 : 0;
-      v = a[((((q * L0 + lz) * L1 + (yh >> 1)) * L2 + (xw >> 1)) * Q1) + j];
+      v = a[(((((long long)q * L0 + lz) * L1 + (yh >> 1)) * L2 + (xw >> 1)) * Q1) + j];
     } else {
       const int c0 = (j << 2) - g.C1;              // first skip channel of this quad
-      const float* bp = b + pix * g.C2 + c0;
+      const float* bp = b + (long long)pix * g.C2 + c0;
       if ((g.C2 & 3) == 0 && c0 + 4 <= g.C2) {
         v = *reinterpret_cast<const float4*>(bp);
       } else {
@@ -684,6 +680,7 @@ upcat_fwd_v4_kernel(const float4* __restrict__ a, const float* __restrict__ b, f
 }
 
 // da (128-bit, C1 % 4 == 0, Cs % 4 == 0): one quad of one parent voxel per thread, the 2^nd children summed in a fixed order
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 upcat_bwd_a_v4_kernel(const float4* __restrict__ dy, float4* __restrict__ da, UcGeom g) {
   const int Q = g.Cs >> 2, Q1 = g.C1 >> 2;
@@ -691,11 +688,11 @@ upcat_bwd_a_v4_kernel(const float4* __restrict__ dy, float4* __restrict__ da, Uc
   const long long total = (long long)g.N * L0 * L1 * L2 * Q1;
   const int nz = g.S[0] > 1 ? 2 : 1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long q = i;
-    const int j = (int)(q % Q1); q /= Q1;
-    const int lx = (int)(q % L2); q /= L2;
-    const int ly = (int)(q % L1); q /= L1;
-    const int lz = (int)(q % L0); q /= L0;
+    IDX q = (IDX)i;
+    const int j = (int)(q % (IDX)Q1); q /= (IDX)Q1;
+    const int lx = (int)(q % (IDX)L2); q /= (IDX)L2;
+    const int ly = (int)(q % (IDX)L1); q /= (IDX)L1;
+    const int lz = (int)(q % (IDX)L0); q /= (IDX)L0;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int dz = 0; dz < nz; ++dz)
 #pragma unroll
@@ -703,7 +700,7 @@ upcat_bwd_a_v4_kernel(const float4* __restrict__ dy, float4* __restrict__ da, Uc
 #pragma unroll
         for (int dxx = 0; dxx < 2; ++dxx) {
           const int zd = g.S[0] > 1 ? 2 * lz + dz : 0;
-          const float4 t = dy[((((q * g.S[0] + zd) * g.S[1] + 2 * ly + dyy) * g.S[2] + 2 * lx + dxx) * Q) + j];
+          const float4 t = dy[(((((long long)q * g.S[0] + zd) * g.S[1] + 2 * ly + dyy) * g.S[2] + 2 * lx + dxx) * Q) + j];
           acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
     da[i] = acc;
@@ -1001,7 +998,10 @@ extern "C" int dfmir_upsample_concat_padded_fwd(const float* a, const float* b, 
   g.Cs = Cs;
   const long long total = (long long)N * g.S[0] * g.S[1] * g.S[2] * Cs;
   if (C1 % 4 == 0 && Cs % 4 == 0 && ((((uintptr_t)a) | ((uintptr_t)y)) & 15) == 0 && (C2 % 4 != 0 || (((uintptr_t)b) & 15) == 0))
-    upcat_fwd_v4_kernel<<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)a, b, (float4*)y, g);
+  {
+    if (total / 4 < (1LL << 32)) upcat_fwd_v4_kernel<unsigned><<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)a, b, (float4*)y, g);
+    else upcat_fwd_v4_kernel<long long><<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)a, b, (float4*)y, g);
+  }
   else
     upcat_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(a, b, y, g);
   DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_fwd");
@@ -1018,7 +1018,9 @@ extern "C" int dfmir_upsample_concat_padded_bwd(const float* dy, float* da, floa
   const long long vox = (long long)g.S[0] * g.S[1] * g.S[2];
   const long long total = (long long)N * (vox >> nd) * C1 + (long long)N * vox * C2;
   if (C1 % 4 == 0 && Cs % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)da)) & 15) == 0) {
-    if (da) upcat_bwd_a_v4_kernel<<<ew_grid((long long)N * (vox >> nd) * (C1 / 4)), 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (float4*)da, g);
+    const long long ta = (long long)N * (vox >> nd) * (C1 / 4);
+    if (da && ta < (1LL << 32)) upcat_bwd_a_v4_kernel<unsigned><<<ew_grid(ta), 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (float4*)da, g);
+    else if (da) upcat_bwd_a_v4_kernel<long long><<<ew_grid(ta), 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (float4*)da, g);
     if (db && C2 > 0) {
       if (da) DFMIR_CHECK_LAUNCH("dfmir_upsample_concat_bwd");
       upcat_bwd_b_kernel<<<ew_grid((long long)N * vox * C2), 256, 0, (cudaStream_t)stream>>>(dy, db, (long long)N * vox, C1, C2, Cs);
