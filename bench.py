@@ -453,7 +453,8 @@ def bench_3d(args, ctx, shape, B, features, cfg_no, steps=None):
     name = "x".join(str(v) for v in shape)
     pk, pk_src = peaks()
     roof = roofline_block(kinds, steps, ms, pk, pk_src,
-                          "conv_umma_halo_kernel (tcgen05 implicit-GEMM 3x3x3 convolution, 5-D TMA halo boxes; forward + data gradient)",
+                          "conv_umma_dmarch_kernel / conv_umma_halo_kernel (tcgen05 implicit-GEMM 3x3x3 convolution: depth-march kernel "
+                          "for the 16..64-channel layers, 5-D TMA halo boxes for the others; forward + data gradient)",
                           f"r2_dominant_kernel_{'3d_128' if six_level else '3d_160'}.json")
     return {
         "value": B * world * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps,
