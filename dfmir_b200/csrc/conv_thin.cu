@@ -11,7 +11,9 @@
 // Data gradients are the same correlations with flipped taps and p' = K-1-p; the head's weight gradient
 // iterates over the input domain with s = dy.  Sources are zero outside their bounds.
 #include "common.cuh"
+#include "umma.cuh"
 #include "dfmir_b200.h"
+#include <stdlib.h>
 
 namespace thin {
 
@@ -88,6 +90,184 @@ thin_expand_kernel(const float* __restrict__ s, const float* __restrict__ w, con
     for (int c = 0; c < CT; ++c)
       if (c0 + c < p.C) op[c] = act_apply(acc[c], p.act);
   }
+}
+
+
+// ------------------------------------------------------------------ expand on the tensor cores (C = 64)
+// The direct kernel above is FMA-bound: 49 x 64 = 3136 multiply-adds per pixel (0.45 ms for 32 images of 256^2 at
+// ~40 % of the fp32 peak) to write 0.54 GB.  As a GEMM it is M = pixels, N = 64, K = 49: the CTA builds the im2col
+// operand of a 16 x 8 pixel tile itself - 128 rows x 56 (49 + 7 zero) taps from a 22 x 14 staged patch of the single
+// source channel, written in the K-major SWIZZLE_128B layout the tcgen05 descriptor expects - and the weights once.
+// Arithmetic stays fp32-class: both operands are split hi = x & ~0x1fff (what the tensor core keeps of an fp32
+// operand), lo = x - hi (exact), and three products hi*hi + hi*lo + lo*hi are accumulated (the dropped lo*lo term is
+// 2^-22 relative) - 21 MMAs of 128 x 64 x 8 per tile, a few hundred clocks against the ~1400 the tile's 32 KB of output
+// take at this SM's share of HBM.  Two CTAs per SM overlap each other's build / MMA / store phases.
+namespace ut = umma;
+
+constexpr int XK = 56;                       // taps padded to whole K = 8 slices
+constexpr int XA_CHUNK = 128 * 128;          // one 32-tap chunk of the 128-row operand
+constexpr int XB_CHUNK = 64 * 128;           // one 32-tap chunk of the 64-channel weight operand
+constexpr int X_SMEM = 4 * XA_CHUNK + 4 * XB_CHUNK + 22 * 16 * 4 + 64 + 1024;
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int kk) {      // byte offset of element (row, kk < 32) in a chunk
+  return (uint32_t)(row * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2)));
+}
+
+__global__ void __launch_bounds__(256, 2)
+thin_expand_umma_kernel(const float* __restrict__ s, const float* __restrict__ w, const float* __restrict__ bias,
+                        float* __restrict__ out, const ThinP p, int ntiles) {
+  constexpr int K = 7, TAPS = 49, TH = 16, TW = 8, PH = TH + K - 1, PW = TW + K - 1;   // 22 x 14 patch
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sAhi = smem;                       // [2 chunks][128 rows][128 B]
+  uint8_t* sAlo = sAhi + 2 * XA_CHUNK;
+  uint8_t* sBhi = sAlo + 2 * XA_CHUNK;        // [2 chunks][64 rows][128 B]
+  uint8_t* sBlo = sBhi + 2 * XB_CHUNK;
+  float* patch = (float*)(sBlo + 2 * XB_CHUNK);            // [22][16]
+  uint64_t* bar = (uint64_t*)(patch + PH * 16);
+  uint32_t* tmem_slot = (uint32_t*)(bar + 1);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  if (t == 0) { ut::mbar_init(bar, 1); ut::fence_barrier_init(); }
+  if (warp == 0) ut::tmem_alloc(tmem_slot, 64u);
+  // weights: B[n = channel][k = tap], hi / lo, zero beyond the 49 taps and p.C channels
+  for (int e = t; e < 64 * 64; e += 256) {
+    const int n = e >> 6, k = e & 63;
+    float v = 0.f;
+    if (k < TAPS && n < p.C) v = __ldg(w + (long long)(p.flip ? TAPS - 1 - k : k) * p.C + n);
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const uint32_t off = (uint32_t)((k >> 5) * XB_CHUNK) + sw128_off(n, k & 31);
+    *(float*)(sBhi + off) = hi;
+    *(float*)(sBlo + off) = v - hi;
+  }
+  ut::tc_fence_before();
+  __syncthreads();
+  ut::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = ut::instr_desc_tf32(128, 64);
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane, th = row >> 3, tw = row & 7;
+  float bv[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) bv[i] = (bias && half * 32 + i < p.C) ? __ldg(bias + half * 32 + i) : 0.f;
+  uint32_t phase = 0;
+  // the source patch of the NEXT tile is fetched into registers while this tile's MMAs run (its global-load latency
+  // was the longest serial piece of a tile)
+  constexpr int PER_T = (PH * PW + 255) / 256;
+  float pre[PER_T];
+  auto fetch = [&](int tile) {
+    int r = tile;
+    const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+    const int th_i = r % p.tiles_h; const int n = r / p.tiles_h;
+    const float* sb = s + (long long)n * p.s_n;
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+      const int e = t + 256 * j;
+      const int pr = e / PW, pc = e - pr * PW;
+      const int ih = th_i * TH + pr - p.ph, iw = tw_i * TW + pc - p.pw;
+      pre[j] = (e < PH * PW && tile < ntiles && ih >= 0 && ih < p.SH && iw >= 0 && iw < p.SW) ? __ldg(sb + ih * p.s_h + iw * p.s_w) : 0.f;
+    }
+  };
+  fetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int r = tile;
+    const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+    const int th_i = r % p.tiles_h; const int n = r / p.tiles_h;
+    const int h0 = th_i * TH, w0 = tw_i * TW;
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+      const int e = t + 256 * j;
+      if (e < PH * PW) patch[(e / PW) * 16 + e % PW] = pre[j];
+    }
+    __syncthreads();
+    // im2col rows: warp -> pixels warp, warp + 8, ...; lane = tap within the 32-tap chunk (conflict-free swizzled stores)
+    for (int it = 0; it < 32; ++it) {
+      const int px = warp + 8 * (it >> 1), c = it & 1;
+      const int k = 32 * c + lane;
+      float v = 0.f;
+      if (k < TAPS) v = patch[((px >> 3) + k / K) * 16 + (px & 7) + k % K];
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      const uint32_t off = (uint32_t)(c * XA_CHUNK) + sw128_off(px, lane);
+      *(float*)(sAhi + off) = hi;
+      *(float*)(sAlo + off) = v - hi;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    if (warp == 0) {         // converged warp, one elected lane issues (no per-MMA ELECT / BRA.U.ANY wrapper)
+      ut::tc_fence_after();
+      const uint64_t ahi = ut::smem_desc_sw128(ut::smem_u32(sAhi), 16, 1024), alo = ut::smem_desc_sw128(ut::smem_u32(sAlo), 16, 1024);
+      const uint64_t bhi = ut::smem_desc_sw128(ut::smem_u32(sBhi), 16, 1024), blo = ut::smem_desc_sw128(ut::smem_u32(sBlo), 16, 1024);
+#pragma unroll
+      for (int seg = 0; seg < 3; ++seg) {
+        const uint64_t ad = seg == 2 ? alo : ahi, bd = seg == 1 ? blo : bhi;
+#pragma unroll
+        for (int ks = 0; ks < XK / 8; ++ks) {
+          const int c = ks >> 2, k = ks & 3;
+          const uint64_t a = ad + (uint64_t)(c * (XA_CHUNK / 16) + 2 * k), b = bd + (uint64_t)(c * (XB_CHUNK / 16) + 2 * k);
+          if ((seg | ks) != 0) ut::umma_tf32_elect<true>(tmem_base, a, b, idesc);
+          else ut::umma_tf32_elect<false>(tmem_base, a, b, idesc);
+        }
+      }
+      ut::umma_commit_elect(bar);
+    }
+    fetch(tile + (int)gridDim.x);
+    ut::mbar_wait(bar, phase);
+    phase ^= 1;
+    ut::tc_fence_after();
+    {
+      // epilogue through shared memory (the operand tiles are free once the MMAs have retired): a thread holds 32
+      // channels of ONE pixel, 256 bytes apart from its neighbour's - stored directly that is 32 half-used sectors per
+      // instruction (lg_throttle-bound: 18 % of HBM); staged, every warp instruction writes 512 contiguous bytes
+      float v[32];
+      ut::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32), v);
+      float* stage = reinterpret_cast<float*>(sAhi);             // [128 pixels][68 floats]: rows padded against bank conflicts
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stage + row * 68 + half * 32 + 4 * i) =
+            make_float4(act_apply(v[4 * i] + bv[4 * i], p.act), act_apply(v[4 * i + 1] + bv[4 * i + 1], p.act),
+                        act_apply(v[4 * i + 2] + bv[4 * i + 2], p.act), act_apply(v[4 * i + 3] + bv[4 * i + 3], p.act));
+      ut::tc_fence_before();
+      __syncthreads();
+      const bool vec = p.C == 64 && (p.o_w & 3) == 0 && (p.o_h & 3) == 0 && (p.o_n & 3) == 0 && (((uintptr_t)out) & 15) == 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = t + 256 * j;                             // float4 index in the tile: pixel * 16 + channel quad
+        const int px = idx >> 4, c4 = idx & 15;
+        const int oh = h0 + (px >> 3), ow = w0 + (px & 7);
+        if (oh >= p.OH || ow >= p.OW) continue;
+        const float4 val = *reinterpret_cast<const float4*>(stage + px * 68 + 4 * c4);
+        float* op = out + (long long)n * p.o_n + (long long)oh * p.o_h + (long long)ow * p.o_w + 4 * c4;
+        if (vec) *reinterpret_cast<float4*>(op) = val;
+        else {
+          if (4 * c4 < p.C) op[0] = val.x;
+          if (4 * c4 + 1 < p.C) op[1] = val.y;
+          if (4 * c4 + 2 < p.C) op[2] = val.z;
+          if (4 * c4 + 3 < p.C) op[3] = val.w;
+        }
+      }
+    }
+    ut::tc_fence_before();
+    __syncthreads();         // the accumulator, the operand tiles and the patch are reused by the next tile
+  }
+  if (warp == 0) ut::tmem_dealloc(tmem_base, 64u);
+}
+
+// expand through the tensor-core kernel when it applies (7 x 7, 17..64 channels); returns false to fall back
+static bool launch_expand_umma(const float* s, const float* w, const float* bias, float* out, ThinP p, cudaStream_t st) {
+  static const int on = getenv("DFMIR_THIN_TC") ? atoi(getenv("DFMIR_THIN_TC")) : 1;
+  if (!on || p.C <= 16 || p.C > 64) return false;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(thin_expand_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM) != cudaSuccess) return false;
+    attr = true;
+  }
+  p.tiles_h = (p.OH + 15) / 16; p.tiles_w = (p.OW + 7) / 8;
+  const long long ntiles = (long long)p.N * p.tiles_h * p.tiles_w;
+  if (ntiles <= 0 || ntiles > 0x7fffffff) return false;
+  long long grid = 2LL * dfmir_num_sms();
+  if (grid > ntiles) grid = ntiles;
+  thin_expand_umma_kernel<<<(unsigned)grid, 256, X_SMEM, st>>>(s, w, bias, out, p, (int)ntiles);
+  return true;
 }
 
 // ------------------------------------------------------------------ reduce: C -> 1 channel
@@ -269,7 +449,8 @@ int dfmir_thin_fwd(const float* x, const float* w, const float* bias, float* y, 
     const unsigned gx = (unsigned)(p.N * p.tiles_h * p.tiles_w);
     // 32 output channels per thread (two CTAs per pixel tile for the 64-channel stem): 3 CTAs resident per SM
     // instead of 1 with 64 accumulators per thread
-    if (p.C > 16) thin::thin_expand_kernel<7, 32><<<dim3(gx, (p.C + 31) / 32), 256, 0, st>>>(x, w, bias, y, p);
+    if (thin::launch_expand_umma(x, w, bias, y, p, st)) {}
+    else if (p.C > 16) thin::thin_expand_kernel<7, 32><<<dim3(gx, (p.C + 31) / 32), 256, 0, st>>>(x, w, bias, y, p);
     else thin::thin_expand_kernel<7, 16><<<dim3(gx, 1), 256, 0, st>>>(x, w, bias, y, p);
   } else {
     if (!vec4_ok(x, d->x_strides, d->Cin) || (((uintptr_t)w) & 15)) return 0;
@@ -295,7 +476,8 @@ int dfmir_thin_dgrad(const float* dy, const float* wt, float* dx, const dfmir_co
     if (d->x_strides[3] != 1) return 0;
     p.C = d->Cin; p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 31) / 32;
     const unsigned gx = (unsigned)(p.N * p.tiles_h * p.tiles_w);
-    if (p.C > 16) thin::thin_expand_kernel<7, 32><<<dim3(gx, (p.C + 31) / 32), 256, 0, st>>>(dy, wt, nullptr, dx, p);
+    if (thin::launch_expand_umma(dy, wt, nullptr, dx, p, st)) {}
+    else if (p.C > 16) thin::thin_expand_kernel<7, 32><<<dim3(gx, (p.C + 31) / 32), 256, 0, st>>>(dy, wt, nullptr, dx, p);
     else thin::thin_expand_kernel<7, 16><<<dim3(gx, 1), 256, 0, st>>>(dy, wt, nullptr, dx, p);
   } else {                   // stem: dy has Cout channels, dx has one
     if (!vec4_ok(dy, d->y_strides, d->Cout) || (((uintptr_t)wt) & 15)) return 0;
