@@ -61,7 +61,10 @@ def test_save_load_networks_round_trip(tmp_path):
     for n in ("G", "F", "R"):
         want, got = getattr(model, "net" + n).state_dict(), getattr(other, "net" + n).state_dict()
         for k in want:                             # Adam's third step: needs the restored moments and step count
-            assert torch.allclose(got[k], want[k], rtol=0, atol=2e-5), (n, k)
+            # conv biases in front of an instance norm have a true gradient of zero: what Adam normalises there is
+            # atomics-order noise, whose sign - and so a +-lr step - may differ between two runs of the same step
+            tol = 1e-3 if (n == "G" and k.endswith(".bias")) else 2e-5
+            assert torch.allclose(got[k], want[k], rtol=0, atol=tol), (n, k)
     assert int(other.optimizer_R.state[next(other.netR.parameters())]["step"]) == 3
 
 
