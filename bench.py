@@ -130,6 +130,12 @@ WORKLOADS_3D = {          # name -> (shape, batch per GPU, features, BASELINE co
 }
 
 
+def workload_name_3d(shape, B, features, cfg_no):
+    name = "x".join(str(v) for v in shape)
+    return (f"3D {name} batch={B}/GPU VoxelMorph-3D ({'6-level' if features == '6level' else 'default'} features) + VecInt + "
+            f"NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[{cfg_no}])")
+
+
 def conv_flops_3d(shape, six_level):
     """VxmDense-3D 128^3 6-level 284.6 GFLOP per pair (95.0 fwd + 189.6 bwd); default features at
     160x192x160 1708.1; both scale with the voxel count."""
@@ -200,13 +206,16 @@ def run_reference(args):
         for name, (shape, _, feats, cfg) in WORKLOADS_3D.items():
             cb = cpu_baseline_3d(shape, feats)
             workloads[name] = {"value": cb["value"], "unit": UNIT, "cpu_baseline": cb,
-                               "config": {"workload": f"3D {name[3:]} VoxelMorph-3D + NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[{cfg}]); CPU sample: batch 1"}}
+                               "config": {"workload": workload_name_3d(shape, WORKLOADS_3D[name][1], feats, cfg), "sample": "1 pair (batch 1), 1 step"}}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"2D {S}x{S} translation+registration fwd/bwd+Adam (BASELINE configs[1]); CPU sample: batch 1 per step",
-                   "batch_per_step": 1},
+        # the arm's workload is the headline workload of `bench.py --impl ours`; a step here is a bounded SAMPLE of it
+        # (one of the batch's pairs: the step is independent per pair except for the batch mean of the losses)
+        "config": {"workload": f"2D {S}x{S} batch={args.batch}/GPU translation+registration fwd/bwd+Adam (BASELINE configs[1])",
+                   "batch_per_gpu": args.batch, "global_batch": args.batch * max(args.gpus, 1), "parallelism": f"dp{max(args.gpus, 1)}",
+                   "sample": "1 pair (batch 1) per step on the host cores"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "workloads": workloads}))
@@ -459,8 +468,7 @@ def bench_3d(args, ctx, shape, B, features, cfg_no, steps=None):
     return {
         "value": B * world * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "ms_per_step": ms / steps, "scaling": "weak", "dtype": "tf32",
-        "config": {"workload": f"3D {name} batch={B}/GPU VoxelMorph-3D ({'6-level' if six_level else 'default'} features) + VecInt + "
-                               f"NCC[9^3] + Grad fwd/bwd+Adam (BASELINE configs[{cfg_no}])",
+        "config": {"workload": workload_name_3d(shape, B, features, cfg_no),
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": graphed,
                    **({"cuda_graph_note": graph_note} if graph_note else {}),
                    "l2_policy": "inputs larger than L2: full-resolution activations are 16-36 channels x 8-20 MB per volume"},
