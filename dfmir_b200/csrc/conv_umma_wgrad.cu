@@ -405,7 +405,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {     // converged warp, elected issue (umma.cuh): no ELECT / BRA.U.ANY loop around every tcgen05.mma
       constexpr uint32_t idesc = instr_desc_tf32(128, BN, 1, 1);   // both operands MN-major
       for (int it = 0; it < iters; ++it) {
         const int s = it % L::STAGES;
@@ -425,14 +425,17 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             for (int ks = 0; ks < L::TW / UMMA_K; ++ks) {
               const int row_x = (kd * L::HH + kh + hy) * L::HW + UMMA_K * ks;     // first voxel of this K slice, tap kw = 0
               const int row_g = hy * L::TW + UMMA_K * ks;
-              umma_tf32(tmem_base + (uint32_t)(a * BN), ad0 + (uint64_t)(8 * row_x), bd0 + (uint64_t)(8 * row_g), idesc,
-                        (uint32_t)((it | hy | ks) != 0));
+              if ((hy | ks) != 0)
+                umma_tf32_elect<true>(tmem_base + (uint32_t)(a * BN), ad0 + (uint64_t)(8 * row_x), bd0 + (uint64_t)(8 * row_g), idesc);
+              else
+                umma_tf32_elect_rt(tmem_base + (uint32_t)(a * BN), ad0 + (uint64_t)(8 * row_x), bd0 + (uint64_t)(8 * row_g), idesc,
+                                   (uint32_t)(it != 0));
             }
           }
         }
-        umma_commit(empty + s);
+        umma_commit_elect(empty + s);
       }
-      umma_commit(tmem_full);
+      umma_commit_elect(tmem_full);
     }
   } else {
     // epilogue: TMEM lane = kw * 32 + (input channel - c0); BN output-channel columns per accumulator
