@@ -90,15 +90,23 @@ __global__ void in_finalize_kernel(const double* __restrict__ sums, float* __res
 // Statistics from the per-row-group sums a convolution epilogue wrote (dfmir_conv_umma_fwd_stats):
 // rows [n][rows_per_image][C] of {sum, sum of squares} over <= 32 voxels each -> stats (mean, rstd), summed in fp64 in a
 // fixed order.  grid (C / 32, N); thread = (channel of the 32-channel group, one of 8 row lanes).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 in_finalize_rows_kernel(const float2* __restrict__ rows, float* __restrict__ stats, int rows_per_image, int C, int HW, float eps) {
-  __shared__ double red[8][32][2];
+  // 32 channels x 32 row lanes: with 128 rows per image a lane adds four independent 8-byte loads (the 8-lane version
+  // walked 16 dependent-latency trips: 19 us per launch for 8 MB)
+  __shared__ double red[32][32][2];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl, n = blockIdx.y;
   double s = 0, ss = 0;
   if (c < C) {
     const float2* rb = rows + (long long)n * rows_per_image * C + c;
-    for (int r = rl; r < rows_per_image; r += 8) {
+    int r = rl;
+    for (; r + 96 < rows_per_image; r += 128) {
+      const float2 v0 = rb[(long long)r * C], v1 = rb[(long long)(r + 32) * C], v2 = rb[(long long)(r + 64) * C], v3 = rb[(long long)(r + 96) * C];
+      s += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+      ss += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+    }
+    for (; r < rows_per_image; r += 32) {
       const float2 v = rb[(long long)r * C];
       s += (double)v.x; ss += (double)v.y;
     }
@@ -107,7 +115,7 @@ in_finalize_rows_kernel(const float2* __restrict__ rows, float* __restrict__ sta
   __syncthreads();
   if (rl == 0 && c < C) {
 #pragma unroll
-    for (int l = 1; l < 8; ++l) { s += red[l][cl][0]; ss += red[l][cl][1]; }
+    for (int l = 1; l < 32; ++l) { s += red[l][cl][0]; ss += red[l][cl][1]; }
     const double m = s / HW;
     double var = ss / HW - m * m;
     if (var < 0) var = 0;
@@ -854,7 +862,7 @@ extern "C" int dfmir_instnorm_fwd_rows(const float* x, const float* res, float* 
   DFMIR_CHECK_ARG(out_pad >= 0 && out_pad < H && out_pad < W && res_pad >= 0, "dfmir_instnorm_fwd_rows: bad padding");
   DFMIR_CHECK_ARG(N <= 65535, "dfmir_instnorm_fwd_rows: batch too large");
   cudaStream_t st = (cudaStream_t)stream;
-  in_finalize_rows_kernel<<<dim3((C + 31) / 32, N), 256, 0, st>>>((const float2*)stat_rows, stats, rows_per_image, C, H * W, eps);
+  in_finalize_rows_kernel<<<dim3((C + 31) / 32, N), 1024, 0, st>>>((const float2*)stat_rows, stats, rows_per_image, C, H * W, eps);
   DFMIR_CHECK_LAUNCH("dfmir_instnorm_fwd_rows(finalize)");
   if (in_v4_ok(C, x, y, res, stats) && H + 2 * out_pad <= 65535) {
     int ach; const int achunk = apply_chunk((H + 2 * out_pad) * (W + 2 * out_pad), N, &ach);
