@@ -568,6 +568,43 @@ blur_down_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
   }
 }
 
+// The same adjoint for even H and W, one 2 x 2 block of dx per thread from the four dy values that touch it: per axis
+//   dx[2i] = 0.5 g[i],  dx[2i+1] = 0.25 (g[i] + g[i+1])  (g[OH] = 0),  dx[1] += 0.25 g[0]  (the reflected index -1)
+// - 4 loads and 4 stores per thread instead of up to 9 gathers per stored element (2.0 ms / step at 1.3 TB/s).
+__device__ __forceinline__ float4 vadd(const float4 a, const float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float vadd(const float a, const float b) { return a + b; }
+__device__ __forceinline__ float4 vscale(const float4 a, const float w) { return make_float4(a.x * w, a.y * w, a.z * w, a.w * w); }
+__device__ __forceinline__ float vscale(const float a, const float w) { return a * w; }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+blur_down_bwd_even_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
+  const long long total = (long long)N * OH * OW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c, j, ii, n;
+    unravel4(i, total < (1LL << 32), C, OW, OH, c, j, ii, n);
+    const T* gb = dy + (long long)n * OH * OW * C + c;
+    const T z = vzero(T());
+    const bool hj = j + 1 < OW, hi = ii + 1 < OH;
+    const T g00 = gb[((long long)ii * OW + j) * C];
+    const T g01 = hj ? gb[((long long)ii * OW + j + 1) * C] : z;
+    const T g10 = hi ? gb[((long long)(ii + 1) * OW + j) * C] : z;
+    const T g11 = (hi && hj) ? gb[((long long)(ii + 1) * OW + j + 1) * C] : z;
+    // w axis: u(row, 2j), u(row, 2j + 1)
+    const float ew = j == 0 ? 0.5f : 0.25f;                 // 0.25 g[j] + (j == 0: the reflected tap adds another 0.25 g[0])
+    const T u0e = vscale(g00, 0.5f), u0o = vadd(vscale(g00, ew), vscale(g01, 0.25f));
+    const T u1e = vscale(g10, 0.5f), u1o = vadd(vscale(g10, ew), vscale(g11, 0.25f));
+    // h axis
+    const float eh = ii == 0 ? 0.5f : 0.25f;
+    T* ob = dx + (long long)n * H * W * C + c;
+    const long long r0 = (long long)(2 * ii) * W + 2 * j, r1 = r0 + W;
+    ob[r0 * C] = vscale(u0e, 0.5f);
+    ob[(r0 + 1) * C] = vscale(u0o, 0.5f);
+    ob[r1 * C] = vadd(vscale(u0e, eh), vscale(u1e, 0.25f));
+    ob[(r1 + 1) * C] = vadd(vscale(u0o, eh), vscale(u1o, 0.25f));
+  }
+}
+
 // per axis: y[2m] = (x[clamp(m-1)] + 3 x[m]) / 4 ; y[2m+1] = (3 x[m] + x[clamp(m+1)]) / 4
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -955,7 +992,13 @@ extern "C" int dfmir_blur_down_fwd(const float* x, float* y, int N, int H, int W
 extern "C" int dfmir_blur_down_bwd(const float* dy, float* dx, int N, int H, int W, int C, void* stream) {
   DFMIR_CHECK_ARG(dy && dx && N > 0 && H > 1 && W > 1 && C > 0, "dfmir_blur_down_bwd: bad argument");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  if (C % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0)
+  const bool even = (H % 2 == 0) && (W % 2 == 0);          // the layers of the generator (256 -> 128 -> 64)
+  if (even && C % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0)
+    blur_down_bwd_even_kernel<float4><<<ew_grid((long long)N * OH * OW * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)dy, (float4*)dx, N, H, W, C / 4, OH, OW);
+  else if (even)
+    blur_down_bwd_even_kernel<float><<<ew_grid((long long)N * OH * OW * C), 256, 0, (cudaStream_t)stream>>>(dy, dx, N, H, W, C, OH, OW);
+  else if (C % 4 == 0 && ((((uintptr_t)dy) | ((uintptr_t)dx)) & 15) == 0)
     blur_down_bwd_kernel<float4><<<ew_grid((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(
         (const float4*)dy, (float4*)dx, N, H, W, C / 4, OH, OW);
   else
