@@ -339,6 +339,173 @@ thin_reduce_kernel(const float* __restrict__ v, const float* __restrict__ w, con
   }
 }
 
+// ------------------------------------------------------------------ weight gradient on the tensor cores (C = 64)
+// dW[tap][c] = sum_p s[p + tap] v[p][c] is a GEMM with the PIXELS as the reduction: M = taps (49 of the 128 operand
+// rows; row 49 is all ones, so the bias gradient sum_p v[p][c] falls out of the same product), N = 64 channels,
+// K = the 64 pixels of an 8 x 8 tile.  A = the im2col patch TRANSPOSED (row = tap, 32 pixels per 128-byte row, K-major
+// SWIZZLE_128B), built by the CTA from a 14 x 14 staged patch; B = the v tile exactly as it lies in memory (row = pixel,
+// 2 column groups of 32 channels: MN-major, written by TMA in SWIZZLE_128B_ATOM_32B).  3xTF32 as in the expand kernel:
+// both operands split hi / lo in shared memory (the split of the TMA-written tile is elementwise, so layout-blind).
+// The accumulator stays in TMEM over all the tiles of the CTA; one atomic pass at the end.
+constexpr int WA_CHUNK = 64 * 128;            // 64 tap rows x 32 pixels (the MMA reads 128 rows: the upper 64 alias what follows)
+constexpr int WB_GROUP = 64 * 128;            // 64 pixels x 32 channels
+constexpr int W_SMEM = 4 * WA_CHUNK + 4 * WB_GROUP + 14 * 16 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(256, 3)
+thin_wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restrict__ s, float* __restrict__ dw,
+                       float* __restrict__ db, const ThinP p, int ntiles) {
+  constexpr int K = 7, TAPS = 49, TH = 8, TW = 8, PH = TH + K - 1, PW = TW + K - 1;    // 14 x 14 patch
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sAhi = smem;                       // [2 chunks][64 rows][128 B]
+  uint8_t* sAlo = sAhi + 2 * WA_CHUNK;
+  uint8_t* sBhi = sAlo + 2 * WA_CHUNK;        // [2 channel groups][64 pixel rows][128 B], written by TMA
+  uint8_t* sBlo = sBhi + 2 * WB_GROUP;
+  float* patch = (float*)(sBlo + 2 * WB_GROUP);             // [14][16]
+  uint64_t* tma_bar = (uint64_t*)(patch + PH * 16);
+  uint64_t* mma_bar = tma_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(mma_bar + 1);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  if (t == 0) { ut::prefetch_tmap(&tmV); ut::mbar_init(tma_bar, 1); ut::mbar_init(mma_bar, 1); ut::fence_barrier_init(); }
+  if (warp == 0) ut::tmem_alloc(tmem_slot, 64u);
+  // constant operand rows: 49 = ones (bias gradient), 50..63 = zero, in both chunks; lo parts zero
+  for (int e = t; e < 2 * 15 * 32; e += 256) {
+    const int c = e / (15 * 32), rr = (e / 32) % 15, kk = e & 31;
+    const uint32_t off = (uint32_t)(c * WA_CHUNK) + sw128_off(TAPS + rr, kk);
+    *(float*)(sAhi + off) = rr == 0 ? 1.f : 0.f;
+    *(float*)(sAlo + off) = 0.f;
+  }
+  ut::tc_fence_before();
+  __syncthreads();
+  ut::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = ut::instr_desc_tf32(128, 64, 0, 1);        // A K-major, B MN-major
+
+  constexpr int PER_T = (PH * PW + 255) / 256;
+  float pre[PER_T];
+  auto coords = [&](int tile, int& n, int& h0, int& w0) {
+    int r = tile;
+    const int tw_i = r % p.tiles_w; r /= p.tiles_w;
+    const int th_i = r % p.tiles_h; n = r / p.tiles_h;
+    h0 = th_i * TH; w0 = tw_i * TW;
+  };
+  auto fetch = [&](int tile) {
+    int n, h0, w0;
+    coords(tile, n, h0, w0);
+    const float* sb = s + (long long)n * p.s_n;
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+      const int e = t + 256 * j;
+      const int pr = e / PW, pc = e - pr * PW;
+      const int ih = h0 + pr - p.ph, iw = w0 + pc - p.pw;
+      pre[j] = (e < PH * PW && tile < ntiles && ih >= 0 && ih < p.SH && iw >= 0 && iw < p.SW) ? __ldg(sb + ih * p.s_h + iw * p.s_w) : 0.f;
+    }
+  };
+  fetch(blockIdx.x);
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    int n, h0, w0;
+    coords(tile, n, h0, w0);
+    if (it > 0) { ut::mbar_wait(mma_bar, (it - 1) & 1); ut::tc_fence_after(); }     // the previous tile's MMAs have read the operands
+    if (t == 0) {
+      ut::mbar_expect_tx(tma_bar, (uint32_t)(2 * WB_GROUP));
+      ut::tma_load_4d(sBhi, &tmV, tma_bar, 0, w0, h0, n);
+      ut::tma_load_4d(sBhi + WB_GROUP, &tmV, tma_bar, 32, w0, h0, n);
+    }
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+      const int e = t + 256 * j;
+      if (e < PH * PW) patch[(e / PW) * 16 + e % PW] = pre[j];
+    }
+    __syncthreads();
+    fetch(tile + (int)gridDim.x);
+    // A rows: (tap, 32-pixel chunk) items over the warps; lane = pixel within the chunk
+    for (int item = warp; item < 2 * TAPS; item += 8) {
+      const int tap = item >> 1, c = item & 1;
+      const int px = 32 * c + lane;
+      const float v = patch[((px >> 3) + tap / K) * 16 + (px & 7) + tap % K];
+      const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      const uint32_t off = (uint32_t)(c * WA_CHUNK) + sw128_off(tap, lane);
+      *(float*)(sAhi + off) = hi;
+      *(float*)(sAlo + off) = v - hi;
+    }
+    ut::mbar_wait(tma_bar, it & 1);
+    // split the v tile in place (elementwise: the swizzled position of an element does not matter)
+    for (int e = t; e < 2 * WB_GROUP / 16; e += 256) {
+      float4 v = *reinterpret_cast<float4*>(sBhi + 16 * e);
+      float4 hi;
+      hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+      hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+      *reinterpret_cast<float4*>(sBhi + 16 * e) = hi;
+      *reinterpret_cast<float4*>(sBlo + 16 * e) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      ut::tc_fence_after();
+      const uint64_t ahi = ut::smem_desc_sw128(ut::smem_u32(sAhi), 16, 1024), alo = ut::smem_desc_sw128(ut::smem_u32(sAlo), 16, 1024);
+      // MN-major operand: 32-channel column groups WB_GROUP apart, 4-row (pixel) groups 512 bytes apart
+      const uint64_t bhi = ut::smem_desc(ut::smem_u32(sBhi), WB_GROUP, 512, ut::LAYOUT_SW128_BASE32B);
+      const uint64_t blo = ut::smem_desc(ut::smem_u32(sBlo), WB_GROUP, 512, ut::LAYOUT_SW128_BASE32B);
+#pragma unroll
+      for (int seg = 0; seg < 3; ++seg) {
+        const uint64_t ad = seg == 2 ? alo : ahi, bd = seg == 1 ? blo : bhi;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {              // 8 pixels per K slice
+          const uint64_t a = ad + (uint64_t)((ks >> 2) * (WA_CHUNK / 16) + 2 * (ks & 3)), b = bd + (uint64_t)(8 * 8 * ks);
+          if ((seg | ks) != 0) ut::umma_tf32_elect<true>(tmem_base, a, b, idesc);
+          else ut::umma_tf32_elect_rt(tmem_base, a, b, idesc, (uint32_t)(it != 0));
+        }
+      }
+      ut::umma_commit_elect(mma_bar);
+    }
+  }
+  // epilogue: TMEM lane = tap (49 = the ones row), column = channel
+  if (it > 0) { ut::mbar_wait(mma_bar, (it - 1) & 1); ut::tc_fence_after(); }
+  if (warp < 2 && it > 0) {
+    const int rowi = warp * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      float v[32];
+      ut::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (rowi < TAPS) {
+        float* dst = dw + (long long)(p.flip ? TAPS - 1 - rowi : rowi) * p.C + c0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < p.C) atomicAdd(dst + i, v[i]);
+      } else if (rowi == TAPS && db) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < p.C) atomicAdd(db + c0 + i, v[i]);
+      }
+    }
+  }
+  ut::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ut::tmem_dealloc(tmem_base, 64u);
+}
+
+static bool launch_wgrad_umma(const float* s, const float* v, float* dw, float* db, ThinP p, cudaStream_t st) {
+  static const int on = getenv("DFMIR_THIN_TC") ? atoi(getenv("DFMIR_THIN_TC")) : 1;
+  if (!on || p.C != 64 || (((uintptr_t)v) & 15) || (p.o_n & 3) || (p.o_h & 3) || (p.o_w & 3)) return false;
+  CUtensorMap tm;
+  const long long as[4] = {p.o_n, p.o_h, p.o_w, 1};
+  if (ut::encode_act_map(&tm, v, as, p.C, p.OW, p.OH, p.N, 8, 8, "dfmir_conv_wgrad(thin)", CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) != DFMIR_OK) return false;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(thin_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM) != cudaSuccess) return false;
+    attr = true;
+  }
+  p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 7) / 8;
+  const long long ntiles = (long long)p.N * p.tiles_h * p.tiles_w;
+  if (ntiles <= 0 || ntiles > 0x7fffffff) return false;
+  long long grid = 3LL * dfmir_num_sms();
+  if (grid > ntiles) grid = ntiles;
+  thin_wgrad_umma_kernel<<<(unsigned)grid, 256, W_SMEM, st>>>(tm, s, dw, db, p, (int)ntiles);
+  return true;
+}
+
 // ------------------------------------------------------------------ weight gradient
 // thread = (channel c, pixel group g); a unit is 8 rows x 32 columns of v's domain, group g owns 8
 // columns.  Per row the thread keeps 8 v values and, per tap row, 8+K-1 source values in registers
@@ -518,7 +685,8 @@ int dfmir_thin_wgrad(const float* x, const float* dy, float* dw, float* db, cons
   int gx = 2 * dfmir_num_sms() / ctiles;
   if (gx > units) gx = units;
   if (gx < 1) gx = 1;
-  thin::thin_wgrad_kernel<7><<<dim3((unsigned)gx, (unsigned)ctiles), 256, 0, st>>>(s, v, dw, d->Cin == 1 ? db : nullptr, p, units);
+  if (!thin::launch_wgrad_umma(s, v, dw, d->Cin == 1 ? db : nullptr, p, st))
+    thin::thin_wgrad_kernel<7><<<dim3((unsigned)gx, (unsigned)ctiles), 256, 0, st>>>(s, v, dw, d->Cin == 1 ? db : nullptr, p, units);
   dfmir_count_launch();
   if (d->Cout == 1 && db) {   // bias gradient of the single output channel: sum of dy (dense (N,OH,OW,1))
     const long long n = (long long)d->N * d->out_shape[0] * d->out_shape[1];
