@@ -475,6 +475,8 @@ class _InstNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, stats = ctx.saved_tensors
         N, H, W, C, relu, out_pad, res_pad, has_res = ctx.meta
+        if dy.is_sparse:          # the layer's only consumer was a PatchNCE tap (last layer of an encoder-only pass)
+            dy = dy.to_dense()
         dy = _f32(dy).contiguous()
         dx = torch.empty_like(x)
         dres = None
@@ -795,8 +797,41 @@ class _GatherSparseFn(torch.autograd.Function):
         return torch.sparse_coo_tensor(idx, _f32(dout).reshape(B * P, C), (B, H, W, C), check_invariants=False), None
 
 
+class _GatherSparsePadFn(torch.autograd.Function):
+    """_GatherSparseFn for a tap that is the interior of a reflect-padded channels-last buffer P (B,H+2p,W+2p,C) - the
+    ResnetBlock outputs: the gradient is a sparse COO tensor on P itself, so that autograd index-adds B*P rows into the
+    dense gradient from the next block instead of zero-filling a dense (B,H,W,C) gradient, scattering into it, zero-filling
+    a padded copy for the slice's backward and adding that (~2 GB of traffic per tapped layer and pass at batch 16)."""
+
+    @staticmethod
+    def forward(ctx, P_cl, ids, pad):
+        _lib.require_cuda(P_cl, ids)
+        B, HP, WP, C = P_cl.shape
+        H, W = HP - 2 * pad, WP - 2 * pad
+        n = ids.numel()
+        ids = ids.to(torch.int64).contiguous()
+        out = torch.empty((B * n, C), dtype=P_cl.dtype, device=P_cl.device)
+        strides = (ctypes.c_longlong * 4)(HP * WP * C, WP * C, C, 1)
+        _lib.call("dfmir_gather_patches_fwd", P_cl[:, pad:HP - pad, pad:WP - pad, :], ids, out, B, n, C, W, strides)
+        ctx.save_for_backward(ids)
+        ctx.meta = (B, C, HP, WP, W, n, pad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        B, C, HP, WP, W, n, pad = ctx.meta
+        b = torch.arange(B, device=ids.device).repeat_interleave(n)
+        idx = torch.stack([b, (ids // W + pad).repeat(B), (ids % W + pad).repeat(B)])
+        return torch.sparse_coo_tensor(idx, _f32(dout).reshape(B * n, C), (B, HP, WP, C), check_invariants=False), None, None
+
+
 def gather_patches(feat, ids):
     """feat (B,C,H,W) logical layout -> (B*P, C) rows at the spatial positions ids."""
+    pad = getattr(feat, "_dfmir_cl_pad", None)   # (P, p): feat is the interior of the padded buffer P (ResnetBlock outputs)
+    if (SPARSE_TAP_GRAD and pad is not None and pad[0].requires_grad and torch.is_grad_enabled() and pad[0].dtype == torch.float32
+            and pad[0].shape[3] == feat.shape[1] and pad[0].shape[1] == feat.shape[2] + 2 * pad[1]):
+        return _GatherSparsePadFn.apply(pad[0], ids, pad[1])
     x_cl = getattr(feat, "_dfmir_cl", None)      # set by ResnetGenerator.forward on taps of plain channels-last outputs
     if (SPARSE_TAP_GRAD and x_cl is not None and x_cl.requires_grad and torch.is_grad_enabled() and x_cl.is_contiguous()
             and x_cl.dtype == torch.float32 and x_cl.shape == (feat.shape[0], feat.shape[2], feat.shape[3], feat.shape[1])):

@@ -209,12 +209,15 @@ class ResnetGenerator(nn.Module):
         class _Stop(Exception):
             pass
 
-        def tap(idx, x_cl):
-            """record the output of reference layer `idx` (channels-last tensor or view)"""
+        def tap(idx, x_cl, padded=None):
+            """record the output of reference layer `idx` (channels-last tensor or view; padded = (P, p) when x_cl is
+            the interior of the reflect-padded buffer P)"""
             if idx in want:
                 v = self._nchw(x_cl)
                 if x_cl._base is None and x_cl.is_contiguous():
                     v._dfmir_cl = x_cl          # lets PatchSampleF's gather return a sparse gradient (functional.gather_patches)
+                elif padded is not None and padded[1] > 0 and padded[0].is_contiguous():
+                    v._dfmir_cl_pad = padded    # the same for an interior view: sparse gradient on the padded buffer
                 feats[idx] = v
             if encode_only and idx == last:
                 raise _Stop()
@@ -244,7 +247,7 @@ class ResnetGenerator(nn.Module):
                 P = Fn.pad_reflect_cl(a, 1)
                 for b in range(nb):
                     op = 1 if b + 1 < nb else 0
-                    P = m[idx].forward_padded(P, op); tap(idx, interior(P, op))
+                    P = m[idx].forward_padded(P, op); tap(idx, interior(P, op), padded=(P, op))
                     idx += 1
                 a = P
             for i in range(nd):

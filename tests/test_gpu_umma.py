@@ -458,6 +458,39 @@ def test_sparse_tap_gradient_equals_dense():
     assert torch.allclose(res[True][1], res[False][1], rtol=0, atol=1e-6)
 
 
+def test_sparse_tap_gradient_on_padded_buffer_equals_dense():
+    """The same for a tap that is the interior of a reflect-padded buffer (the ResnetBlock outputs, layers 12 / 16 of the
+    generator): sparse gradient on the padded buffer itself vs the dense path through the slice's backward."""
+    import dfmir_b200.functional as Fn
+    r = gi.rng(1401)
+    B, H, W, C, P, pad = 2, 12, 20, 16, 48, 1
+    x = torch.from_numpy(r.standard_normal((B, H + 2 * pad, W + 2 * pad, C)).astype(np.float32)).cuda()
+    ids = torch.from_numpy(r.permutation(H * W)[:P]).cuda()
+    gw = torch.from_numpy(r.standard_normal((B * P, C)).astype(np.float32)).cuda()
+    gd = torch.from_numpy(r.standard_normal(tuple(x.shape)).astype(np.float32)).cuda()
+    res = {}
+    for sparse in (True, False):
+        prev = Fn.SPARSE_TAP_GRAD
+        Fn.SPARSE_TAP_GRAD = sparse
+        try:
+            xl = x.clone().requires_grad_()
+            Pb = xl * 1.0
+            v = Pb[:, pad:H + pad, pad:W + pad, :].permute(0, 3, 1, 2)
+            v._dfmir_cl_pad = (Pb, pad)
+            rows = Fn.gather_patches(v, ids)
+            ((rows * gw).sum() + (Pb * gd).sum()).backward()
+            res[sparse] = (rows.detach().clone(), xl.grad.clone())
+        finally:
+            Fn.SPARSE_TAP_GRAD = prev
+    assert torch.equal(res[True][0], res[False][0])
+    want = gd.clone()
+    inner = want[:, pad:H + pad, pad:W + pad, :].reshape(B, H * W, C).clone()
+    inner[:, ids, :] += gw.view(B, P, C)
+    want[:, pad:H + pad, pad:W + pad, :] = inner.view(B, H, W, C)
+    assert torch.allclose(res[False][1], want, rtol=0, atol=1e-6)
+    assert torch.allclose(res[True][1], want, rtol=0, atol=1e-6)
+
+
 @pytest.mark.parametrize("nd,N,Cin,Cout,S", [(3, 1, 2, 16, (16, 24, 32)), (3, 2, 16, 32, (8, 16, 24)), (3, 1, 32, 64, (8, 8, 16)),
                                              (2, 2, 2, 16, (64, 48)), (2, 1, 16, 32, (32, 40)), (2, 2, 64, 64, (16, 24))])
 def test_strided_encoder_conv_on_tensor_cores(nd, N, Cin, Cout, S):
