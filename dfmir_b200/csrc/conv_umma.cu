@@ -544,8 +544,8 @@ __device__ __forceinline__ void umma_tf32_c(uint32_t tmem_d, uint64_t adesc, uin
 template <int BN, bool RES = false>
 struct DmCfg {
   static constexpr int R = 512 / BN;                      // accumulator slots
-  static constexpr int RES_CHUNKS = BN == 16 ? 2 : 1;     // 110.6 KB of weights either way
-  static constexpr int AST = 4;                           // activation stages (one input slice x 32 channels each)
+  static constexpr int RES_CHUNKS = BN == 16 ? 2 : 1;     // 110.6 KB of weights (BN = 16, 32), 162 KB at BN = 48
+  static constexpr int AST = (RES && BN == 48) ? 2 : 4;   // activation stages (one input slice x 32 channels each)
   static constexpr int BST = BN <= 32 ? 9 : 3;            // weight stages (one in-plane tap x 3 depth taps each); divides 9, so
                                                           // that the stage of a tap is a compile-time constant
   static constexpr int NB = 4;                            // steps the epilogue may lag behind the MMA issuer
@@ -556,7 +556,8 @@ struct DmCfg {
   static constexpr int B_BYTES = RES ? RES_CHUNKS * 9 * B_ST : BST * B_ST;
   static constexpr int SMEM = AST * A_ST + B_BYTES + NBARS * 8 + 16 + 1024;
   static_assert(R >= NB + 4, "the ring must hold the slots in flight");
-  static_assert(!RES || BN <= 32, "resident weights: 16 / 32-channel tiles");
+  static_assert(!RES || BN <= 48, "resident weights: 16 / 32 / 48-channel tiles");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
 };
 
 struct DmP {
@@ -1302,6 +1303,9 @@ int run_umma(const float* act, const Strides5& as, int ID, int IH, int IW, const
       (long long)p.N * p.D * p.H * p.W >= 8192) {
     static const int res = getenv("DFMIR_UMMA_DMARCH_RES") ? atoi(getenv("DFMIR_UMMA_DMARCH_RES")) : 1;
     const int cch = (p.Cin + KCH - 1) / KCH;
+    // 33..48 output channels (the data gradient of the 36-channel concat layer) with one input chunk: 48-column tiles keep
+    // the whole weight tensor resident (as 64-column tiles they streamed 216 KB of weights per input slice: 46 % L2 throughput)
+    if (BN == 64 && p.Cout <= 48 && res && cch == 1) return launch_dmarch<48, true>(act, as, ID, IH, IW, w, bias, y, p, st, who);
     if (BN == 64) return launch_dmarch<64, false>(act, as, ID, IH, IW, w, bias, y, p, st, who);
     if (BN == 32) return res && cch <= DmCfg<32, true>::RES_CHUNKS ? launch_dmarch<32, true>(act, as, ID, IH, IW, w, bias, y, p, st, who)
                                                                    : launch_dmarch<32, false>(act, as, ID, IH, IW, w, bias, y, p, st, who);
