@@ -38,3 +38,16 @@ def test_packed_weight_purges_dead_entries():
     for _ in range(300):
         Fn.packed_weight(torch.randn(2, 2, 1, 1))    # temporaries (linear() passes views): their entries die with them
     assert len(Fn._pack_cache) <= 260
+
+
+def test_fused_adam_rejects_cpu_tensors():
+    """dfmir_b200.optim.FusedAdam has no CPU path: parameters on the host raise DfmirError at step() (no silent fallback)."""
+    import pytest
+    import torch
+    from dfmir_b200 import _lib
+    from dfmir_b200.optim import FusedAdam
+    p = torch.zeros(8, requires_grad=True)
+    p.grad = torch.ones(8)
+    opt = FusedAdam([p], lr=1e-3)
+    with pytest.raises((_lib.DfmirError, RuntimeError)):
+        opt.step()
