@@ -52,7 +52,11 @@ class FusedAdam(torch.optim.Optimizer):
                 raise _lib.DfmirError("FusedAdam: parameters and gradients must be dense contiguous float32 CUDA tensors")
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]['exp_avg'].data_ptr(), self.state[p]['exp_avg_sq'].data_ptr(),
                      p.numel()) for p in ps)
-        hit = self._tables.get(gi)
+        # two sets of table buffers per group: eager steps and graph captures never share one, so that an eager step taken
+        # after a capture (different gradient addresses) cannot rewrite the pinned tables a captured graph re-uploads
+        capturing = torch.cuda.is_current_stream_capturing()
+        slot = (gi, capturing)
+        hit = self._tables.get(slot)
         if hit is not None and hit[0] == key:
             return hit
         # The tables go up through pinned host buffers with asynchronous copies: legal inside a CUDA-graph capture
@@ -64,12 +68,18 @@ class FusedAdam(torch.optim.Optimizer):
         dev = allp[0].device
         cap_t = 40 * len(allp)
         cap_w = sum((p.numel() + chunk - 1) // chunk for p in allp)
-        if hit is None:
-            bufs = (torch.zeros(cap_t, dtype=torch.uint8).pin_memory(), torch.zeros((max(cap_w, 1), 2), dtype=torch.int32).pin_memory(),
+        def alloc():
+            return (torch.zeros(cap_t, dtype=torch.uint8).pin_memory(), torch.zeros((max(cap_w, 1), 2), dtype=torch.int32).pin_memory(),
                     torch.zeros(cap_t, dtype=torch.uint8, device=dev), torch.zeros((max(cap_w, 1), 2), dtype=torch.int32, device=dev))
+        if hit is None:
+            if capturing:
+                raise _lib.DfmirError("FusedAdam: run one eager step before capturing (the table buffers are allocated there)")
+            bufs = alloc()
+            if (gi, True) not in self._tables:       # the capture set, allocated outside any capture
+                self._tables[(gi, True)] = (None, None, None, 0, alloc())
         else:
             bufs = hit[4]
-            if not torch.cuda.is_current_stream_capturing():
+            if not capturing:
                 torch.cuda.current_stream(dev).synchronize()      # an earlier upload may still be reading the pinned buffers
         h_tab, h_work, t_tab, w_tab = bufs
         rec = b"".join(struct.pack("<QQQQq", *k) for k in key)
@@ -82,7 +92,7 @@ class FusedAdam(torch.optim.Optimizer):
         t_tab.copy_(h_tab, non_blocking=True)
         w_tab.copy_(h_work, non_blocking=True)
         hit = (key, t_tab, w_tab, len(work), bufs)
-        self._tables[gi] = hit
+        self._tables[slot] = hit
         return hit
 
     @torch.no_grad()
