@@ -111,4 +111,7 @@ class FusedAdam(torch.optim.Optimizer):
             dbl = ctypes.c_double
             _lib.call("dfmir_adam_multi", t_tab, w_tab, n_work, step, lr_dev, dbl(0.0 if lr_dev is not None else float(lr)),
                       dbl(float(group['betas'][0])), dbl(float(group['betas'][1])), dbl(float(group['eps'])))
+            # the kernel writes the parameters behind autograd's back: bump their version counters as torch.optim.Adam's
+            # in-place ops do (kernel-layout weight copies are cached per version; saved-tensor checks rely on it)
+            torch.autograd.graph.increment_version([p for p in group['params'] if p.grad is not None])
         return loss

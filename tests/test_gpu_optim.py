@@ -94,3 +94,25 @@ def test_fused_adam_in_cuda_graph():
         graph.replay(); ob.step()
     for a, b in zip(pa, pb):
         assert torch.allclose(a, b, rtol=2e-5, atol=2e-7)
+
+
+def test_fused_adam_step_invalidates_cached_weight_layouts():
+    """The kernel writes the parameters behind autograd's back: step() bumps their version counters, so a kernel-layout
+    copy cached by a no-grad forward (functional.packed_weight, keyed on the version) is rebuilt after an update."""
+    from dfmir_b200 import functional as Fn
+    from dfmir_b200.optim import FusedAdam
+    w = torch.randn(8, 4, 3, 3, device="cuda").requires_grad_()
+    frozen = torch.randn(5, device="cuda").requires_grad_()        # no gradient: untouched, version unchanged
+    opt = FusedAdam([w, frozen], lr=1e-2, betas=(0.5, 0.999))
+    with torch.no_grad():
+        before = Fn.packed_weight(w)
+        assert Fn.packed_weight(w) is before
+    v0, f0 = w._version, frozen._version
+    w.grad = torch.ones_like(w)
+    opt.step()
+    assert w._version > v0 and frozen._version == f0
+    with torch.no_grad():
+        after = Fn.packed_weight(w)
+    assert after is not before
+    assert torch.equal(after, w.detach().reshape(8, 4, 9).permute(2, 1, 0).contiguous())
+    assert not torch.equal(after, before)
